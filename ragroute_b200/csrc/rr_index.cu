@@ -1,0 +1,1025 @@
+// B1: flat inner-product index (drop-in for faiss IndexFlatIP as the reference uses
+// it: /root/reference/ragroute/data_source.py:71,158,186,203).
+//
+// Storage: two 16-bit planes per corpus (see rr_common.cuh) = 4 bytes / element,
+// the same footprint as FAISS' fp32 rows, of which a scan streams only 2.
+//
+// Search pipeline for a chunk of queries (all on one stream, no host sync):
+//   prep      fp32 queries -> bf16 tile (+ L2 norms for the certificate)
+//   tc scan   rr_scan_tc.cu: TMA + tcgen05 scores, per-warp top-16 lists
+//   finalize  per query: radix-select the kprime best bf16 candidates, rescore
+//             them exactly (fp32 rows rebuilt from the planes, fp64 accumulate),
+//             sort, and CERTIFY: every row that is not a candidate has bf16 score
+//             <= bound, hence exact score <= bound + eps(|q|, max|x|, d); the
+//             result is accepted iff the k-th exact score is above that.
+//   exact     queries whose certificate failed are rescanned with the exact
+//             kernel (lists of depth 32 >= k, so unconditional) and finalized.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "rr_index_internal.cuh"
+#include "rr_topm.cuh"
+
+// ------------------------------------------------------------------ kernels --
+
+// index.add: fp32 rows -> hi/lo planes (+ zero padding to d_pad) and max row norm.
+// one warp per row
+__global__ void __launch_bounds__(256)
+rr_split_rows_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
+                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                     uint32_t* __restrict__ max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    float block_max = 0.f;
+    for (int64_t row = warp; row < n; row += n_warps) {
+        const float* xr = x + row * d;
+        uint16_t* hr = hi + row * d_pad;
+        uint16_t* lr = lo + row * d_pad;
+        float ss = 0.f;
+        for (int e = lane; e < d_pad; e += 32) {
+            uint16_t h = 0, l = 0x8000u;  // joins back to +0.0f
+            if (e < d) {
+                const float v = xr[e];
+                rr_split_f32(v, h, l);
+                ss = fmaf(v, v, ss);
+            }
+            hr[e] = h;
+            lr[e] = l;
+        }
+        ss = rr_warp_sum(ss);
+        block_max = fmaxf(block_max, ss);
+    }
+    if (lane == 0 && block_max > 0.f) {
+        // upper bound of the row norm: sqrt rounded up a little
+        const float nr = sqrtf(block_max) * 1.000001f;
+        atomicMax(max_norm_bits, __float_as_uint(nr));  // positive floats order as uints
+    }
+}
+
+__global__ void __launch_bounds__(256)
+rr_join_rows_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                    int64_t row0, int64_t n, int d, int d_pad, float* __restrict__ out) {
+    const int64_t total = n * d;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / d;
+        const int e = (int)(i - r * d);
+        const int64_t o = (row0 + r) * d_pad + e;
+        const uint32_t b = (((uint32_t)hi[o] << 16) | lo[o]) - 0x8000u;
+        out[i] = __uint_as_float(b);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
+    // faiss fvec_renorm_L2: x /= sqrt(sum x^2) when the norm is positive
+    const int64_t row = blockIdx.x;
+    if (row >= n) return;
+    float* xr = x + row * d;
+    __shared__ float part[4];
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) ss = fmaf(xr[e], xr[e], ss);
+    ss = rr_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    const float tot = part[0] + part[1] + part[2] + part[3];
+    if (tot > 0.f) {
+        const float inv = 1.0f / sqrtf(tot);
+        for (int e = threadIdx.x; e < d; e += blockDim.x) xr[e] *= inv;
+    }
+}
+
+// Control block of one query chunk (device memory, zeroed per chunk).
+struct rr_chunk_ctl {
+    int n_fail;      // queries needing the exact path
+    int any_active;  // at least one query is routed to this source
+};
+
+// fp32 queries -> bf16 tile rows (zero padded to d_pad; rows >= nq zeroed), norms,
+// activity flags.  grid = nq_pad blocks.
+__global__ void __launch_bounds__(128)
+rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
+                       const uint8_t* __restrict__ mask, int64_t mask_stride,
+                       uint16_t* __restrict__ qbf16, float* __restrict__ qnorm,
+                       uint8_t* __restrict__ active, uint8_t* __restrict__ fail_flags,
+                       int* __restrict__ fail_list, rr_chunk_ctl* ctl, int exact_all) {
+    const int b = blockIdx.x;
+    uint16_t* out = qbf16 + (int64_t)b * d_pad;
+    if (b >= nq) {
+        for (int e = threadIdx.x; e < d_pad; e += blockDim.x) out[e] = 0;
+        if (threadIdx.x == 0) active[b] = 0;
+        return;
+    }
+    const bool act = mask ? (mask[(int64_t)b * mask_stride] != 0) : true;
+    const float* qr = q + (int64_t)b * d;
+    __shared__ float part[4];
+    float ss = 0.f;
+    for (int e = threadIdx.x; e < d_pad; e += blockDim.x) {
+        uint16_t h = 0, l = 0;
+        if (e < d && act) {
+            const float v = qr[e];
+            rr_split_f32(v, h, l);
+            ss = fmaf(v, v, ss);
+        }
+        (void)l;
+        out[e] = h;
+    }
+    ss = rr_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        qnorm[b] = sqrtf(part[0] + part[1] + part[2] + part[3]) * 1.000001f;
+        active[b] = act ? 1 : 0;
+        fail_flags[b] = 0;
+        if (act) {
+            ctl->any_active = 1;
+            if (exact_all) {
+                fail_flags[b] = 1;
+                fail_list[atomicAdd(&ctl->n_fail, 1)] = b;
+            }
+        }
+    }
+}
+
+// Exact scan over the queries in fail_list[sub*qsub ...): fp32 rows rebuilt from
+// the planes, products and sums in fp64 (each product of two fp32 is exact in
+// fp64), score rounded once to fp32.  One warp per row; per-warp lists of depth
+// 32 per query, merged per block at the end.
+// cand layout: [query][block][32]
+template <int QSUB>
+__global__ void __launch_bounds__(RR_EXACT_WARPS * 32)
+rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
+                     int64_t n_rows, int d_pad, const float* __restrict__ q, int d,
+                     const int* __restrict__ fail_list, const rr_chunk_ctl* __restrict__ ctl,
+                     int sub, int qsub, float* __restrict__ cand_s,
+                     uint32_t* __restrict__ cand_r, int64_t cand_stride) {
+    const int n_fail = ctl->n_fail;
+    const int q0 = sub * qsub;
+    if (q0 >= n_fail) return;
+    const int nq = min(qsub, n_fail - q0);
+    constexpr int M = RR_EXACT_LIST_DEPTH;
+    constexpr int W = RR_EXACT_WARPS;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* qs = reinterpret_cast<float*>(smem_raw);                       // [qsub][d_pad]
+    float* ls = qs + (size_t)qsub * d_pad;                                // [W][qsub][M]
+    uint32_t* lr = reinterpret_cast<uint32_t*>(ls + (size_t)W * qsub * M);  // [W][qsub][M]
+    float* thr = reinterpret_cast<float*>(lr + (size_t)W * qsub * M);     // [W][qsub]
+    int* qid = reinterpret_cast<int*>(thr + W * qsub);                    // [qsub]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < nq) qid[tid] = fail_list[q0 + tid];
+    __syncthreads();
+    for (int i = tid; i < nq * d_pad; i += blockDim.x) {
+        const int j = i / d_pad, e = i - j * d_pad;
+        qs[i] = (e < d) ? q[(int64_t)qid[j] * d + e] : 0.f;
+    }
+    for (int i = tid; i < W * qsub * M; i += blockDim.x) {
+        ls[i] = RR_NEG_INF;
+        lr[i] = RR_NO_ROW;
+    }
+    for (int i = tid; i < W * qsub; i += blockDim.x) thr[i] = RR_NEG_INF;
+    __syncthreads();
+
+    const int64_t gw = (int64_t)blockIdx.x * W + w;
+    const int64_t GW = (int64_t)gridDim.x * W;
+    const int n_chunks = (d_pad + 255) >> 8;
+    for (int64_t row = gw; row < n_rows; row += GW) {
+        double acc[QSUB];
+#pragma unroll
+        for (int j = 0; j < QSUB; ++j) acc[j] = 0.0;
+        const uint4* hrow = reinterpret_cast<const uint4*>(hi + row * d_pad);
+        const uint4* lrow = reinterpret_cast<const uint4*>(lo + row * d_pad);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int e0 = c * 256 + lane * 8;
+            if (e0 < d_pad) {
+                const uint4 hv = __ldg(hrow + (e0 >> 3));
+                const uint4 lv = __ldg(lrow + (e0 >> 3));
+                float xv[8];
+                float2 t;
+                t = rr_join_f32x2(hv.x, lv.x); xv[0] = t.x; xv[1] = t.y;
+                t = rr_join_f32x2(hv.y, lv.y); xv[2] = t.x; xv[3] = t.y;
+                t = rr_join_f32x2(hv.z, lv.z); xv[4] = t.x; xv[5] = t.y;
+                t = rr_join_f32x2(hv.w, lv.w); xv[6] = t.x; xv[7] = t.y;
+#pragma unroll
+                for (int j = 0; j < QSUB; ++j) {
+                    if (j < nq) {
+                        const float4 qa = *reinterpret_cast<const float4*>(qs + (size_t)j * d_pad + e0);
+                        const float4 qb = *reinterpret_cast<const float4*>(qs + (size_t)j * d_pad + e0 + 4);
+                        double a = acc[j];
+                        a = fma((double)xv[0], (double)qa.x, a);
+                        a = fma((double)xv[1], (double)qa.y, a);
+                        a = fma((double)xv[2], (double)qa.z, a);
+                        a = fma((double)xv[3], (double)qa.w, a);
+                        a = fma((double)xv[4], (double)qb.x, a);
+                        a = fma((double)xv[5], (double)qb.y, a);
+                        a = fma((double)xv[6], (double)qb.z, a);
+                        a = fma((double)xv[7], (double)qb.w, a);
+                        acc[j] = a;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < QSUB; ++j) {
+            if (j < nq) {
+                const float v = (float)rr_warp_sum(acc[j]);
+                const int li = (w * qsub + j);
+                if (v > thr[li]) {  // warp-uniform
+                    float es = ls[(size_t)li * M + lane];
+                    uint32_t er = lr[(size_t)li * M + lane];
+                    rr_list_insert(es, er, v, (uint32_t)row, M, lane);
+                    ls[(size_t)li * M + lane] = es;
+                    lr[(size_t)li * M + lane] = er;
+                    const float tail = __shfl_sync(RR_FULL, es, M - 1);
+                    const uint32_t tail_r = __shfl_sync(RR_FULL, er, M - 1);
+                    if (lane == 0) thr[li] = (tail_r != RR_NO_ROW) ? tail : RR_NEG_INF;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // block merge: warp (j % W) folds the W lists of query j
+    for (int j = w; j < nq; j += W) {
+        float es = ls[(size_t)(0 * qsub + j) * M + lane];
+        uint32_t er = lr[(size_t)(0 * qsub + j) * M + lane];
+        for (int w2 = 1; w2 < W; ++w2) {
+            const float cs = ls[(size_t)(w2 * qsub + j) * M + lane];
+            const uint32_t cr = lr[(size_t)(w2 * qsub + j) * M + lane];
+            rr_list_merge_sorted(es, er, cs, cr, M, lane);
+        }
+        const int64_t o = (int64_t)qid[j] * cand_stride + (int64_t)blockIdx.x * M + lane;
+        cand_s[o] = es;
+        cand_r[o] = er;
+    }
+}
+
+// Per-query finalize.  RESCORE = true: candidates carry bf16 scores (tc scan);
+// select kprime by score, rescore exactly, certify.  RESCORE = false: candidates
+// carry exact scores (exact scan); select the k best by (score, row).
+struct rr_finalize_args {
+    const float* cand_s;
+    const uint32_t* cand_r;
+    int64_t cand_stride;
+    int n_lists;
+    int depth;
+    int k;
+    int kprime;
+    const float* q;  // [nq, d]
+    const float* qnorm;
+    const uint16_t* hi;
+    const uint16_t* lo;
+    int d;
+    int d_pad;
+    const uint32_t* max_norm_bits;
+    int64_t id_offset;
+    float* D;    // row qi at D + qi * out_stride
+    int64_t* I;
+    int64_t out_stride;
+    const uint8_t* active;
+    uint8_t* fail_flags;
+    int* fail_list;
+    rr_chunk_ctl* ctl;
+    int* nfail_total;
+    int pad_inactive;  // exact-only pipeline: the exact finalize also pads unrouted queries
+};
+
+constexpr int RR_FIN_THREADS = 256;
+constexpr int RR_FIN_MAXSEL = 256;
+
+template <bool RESCORE>
+__global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize_args a) {
+    const int qi = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    float* Dq = a.D + (int64_t)qi * a.out_stride;
+    int64_t* Iq = a.I + (int64_t)qi * a.out_stride;
+    if (RESCORE) {
+        if (!a.active[qi]) {  // not routed to this source: padding row, as faiss pads
+            for (int i = tid; i < a.k; i += blockDim.x) {
+                Dq[i] = -3.402823466e+38f;
+                Iq[i] = -1;
+            }
+            return;
+        }
+    } else {
+        if (!a.fail_flags[qi]) {
+            if (a.pad_inactive && !a.active[qi]) {
+                for (int i = tid; i < a.k; i += blockDim.x) {
+                    Dq[i] = -3.402823466e+38f;
+                    Iq[i] = -1;
+                }
+            }
+            return;
+        }
+    }
+
+    __shared__ uint32_t hist[256];
+    __shared__ unsigned long long s_prefix, s_mask;
+    __shared__ int s_remaining, s_cnt_gt, s_cnt_eq, s_nvalid;
+    __shared__ float s_red[RR_FIN_THREADS / 32];
+    __shared__ float sel_s[RR_FIN_MAXSEL];
+    __shared__ uint32_t sel_r[RR_FIN_MAXSEL];
+    extern __shared__ __align__(16) float q_sm[];  // [d_pad] (RESCORE only)
+
+    const float* cs = a.cand_s + (int64_t)qi * a.cand_stride;
+    const uint32_t* cr = a.cand_r + (int64_t)qi * a.cand_stride;
+    const int n_cand = a.n_lists * a.depth;
+
+    if (tid == 0) {
+        s_prefix = 0ull;
+        s_mask = 0ull;
+        s_cnt_gt = 0;
+        s_cnt_eq = 0;
+        s_nvalid = 0;
+    }
+    if (RESCORE) {
+        const float* qr = a.q + (int64_t)qi * a.d;
+        for (int e = tid; e < a.d_pad; e += blockDim.x) q_sm[e] = (e < a.d) ? qr[e] : 0.f;
+    }
+    __syncthreads();
+
+    // T = largest tail of a full list (every dropped row scores <= T); n_valid
+    float T = RR_NEG_INF;
+    int nv = 0;
+    for (int l = tid; l < a.n_lists; l += blockDim.x) {
+        const int64_t o = (int64_t)l * a.depth + a.depth - 1;
+        if (cr[o] != RR_NO_ROW) T = fmaxf(T, cs[o]);
+    }
+    for (int i = tid; i < n_cand; i += blockDim.x) nv += (cr[i] != RR_NO_ROW);
+    T = rr_warp_max(T);
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(RR_FULL, nv, o);
+    if (lane == 0) {
+        s_red[w] = T;
+        atomicAdd(&s_nvalid, nv);
+    }
+    __syncthreads();
+    T = s_red[0];
+    for (int i = 1; i < RR_FIN_THREADS / 32; ++i) T = fmaxf(T, s_red[i]);
+    const int n_valid = s_nvalid;
+    const int want = RESCORE ? min(a.kprime, RR_FIN_MAXSEL) : a.k;
+    const int kp = min(want, n_valid);
+    __syncthreads();
+    if (tid == 0) s_remaining = kp;
+    __syncthreads();
+
+    // radix select of the kp-th largest key (8 bits per pass, MSB first)
+    constexpr int NPASS = RESCORE ? 4 : 8;
+    float t_rest = RR_NEG_INF;
+    if (kp > 0) {
+        for (int pass = 0; pass < NPASS; ++pass) {
+            const int shift = (NPASS - 1 - pass) * 8;
+            hist[tid] = 0;  // RR_FIN_THREADS == 256
+            __syncthreads();
+            const unsigned long long prefix = s_prefix, mask = s_mask;
+            for (int i = tid; i < n_cand; i += blockDim.x) {
+                const uint32_t r = cr[i];
+                if (r == RR_NO_ROW) continue;
+                unsigned long long key = rr_float_key(cs[i]);
+                if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
+                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFull], 1u);
+            }
+            __syncthreads();
+            if (w == 0) {
+                // lane L owns digits 255-8L .. 248-8L (descending)
+                const uint32_t rem = (uint32_t)s_remaining;
+                __syncwarp();
+                uint32_t c[8];
+                uint32_t tot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    c[j] = hist[255 - (lane * 8 + j)];
+                    tot += c[j];
+                }
+                uint32_t incl = tot;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(RR_FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                const uint32_t excl = incl - tot;
+                if (excl < rem && rem <= incl) {  // exactly one lane
+                    uint32_t run = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (run < rem && rem <= run + c[j]) {
+                            const unsigned long long digit = 255 - (lane * 8 + j);
+                            s_prefix = prefix | (digit << shift);
+                            s_mask = mask | (0xFFull << shift);
+                            s_remaining = (int)(rem - run);
+                        }
+                        run += c[j];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // gather: keys above the kp-th all go in; equal keys fill the remaining slots
+        const unsigned long long kth = s_prefix;
+        const int n_eq_take = s_remaining;
+        const int n_gt = kp - n_eq_take;
+        for (int i = tid; i < n_cand; i += blockDim.x) {
+            const uint32_t r = cr[i];
+            if (r == RR_NO_ROW) continue;
+            const float s = cs[i];
+            unsigned long long key = rr_float_key(s);
+            if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
+            if (key > kth) {
+                const int p = atomicAdd(&s_cnt_gt, 1);
+                sel_s[p] = s;
+                sel_r[p] = r;
+            } else if (key == kth) {
+                const int p = atomicAdd(&s_cnt_eq, 1);
+                if (p < n_eq_take) {
+                    sel_s[n_gt + p] = s;
+                    sel_r[n_gt + p] = r;
+                }
+            }
+        }
+        if (n_valid > kp) t_rest = rr_key_float((uint32_t)(RESCORE ? kth : (kth >> 32)));
+    }
+    // pad the selection to a power of two for the sort
+    int kp_pad = 1;
+    while (kp_pad < kp) kp_pad <<= 1;
+    if (kp_pad < 32) kp_pad = 32;
+    __syncthreads();
+    for (int i = kp + tid; i < kp_pad; i += blockDim.x) {
+        sel_s[i] = RR_NEG_INF;
+        sel_r[i] = RR_NO_ROW;
+    }
+    __syncthreads();
+
+    if (RESCORE) {
+        // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation
+        for (int i = w; i < kp; i += RR_FIN_THREADS / 32) {
+            const int64_t row = sel_r[i];
+            const uint4* hrow = reinterpret_cast<const uint4*>(a.hi + row * a.d_pad);
+            const uint4* lrow = reinterpret_cast<const uint4*>(a.lo + row * a.d_pad);
+            double acc = 0.0;
+            for (int e0 = lane * 8; e0 < a.d_pad; e0 += 256) {
+                const uint4 hv = __ldg(hrow + (e0 >> 3));
+                const uint4 lv = __ldg(lrow + (e0 >> 3));
+                const float4 qa = *reinterpret_cast<const float4*>(q_sm + e0);
+                const float4 qb = *reinterpret_cast<const float4*>(q_sm + e0 + 4);
+                float2 t;
+                t = rr_join_f32x2(hv.x, lv.x);
+                acc = fma((double)t.x, (double)qa.x, acc);
+                acc = fma((double)t.y, (double)qa.y, acc);
+                t = rr_join_f32x2(hv.y, lv.y);
+                acc = fma((double)t.x, (double)qa.z, acc);
+                acc = fma((double)t.y, (double)qa.w, acc);
+                t = rr_join_f32x2(hv.z, lv.z);
+                acc = fma((double)t.x, (double)qb.x, acc);
+                acc = fma((double)t.y, (double)qb.y, acc);
+                t = rr_join_f32x2(hv.w, lv.w);
+                acc = fma((double)t.x, (double)qb.z, acc);
+                acc = fma((double)t.y, (double)qb.w, acc);
+            }
+            acc = rr_warp_sum(acc);
+            if (lane == 0) sel_s[i] = (float)acc;
+        }
+        __syncthreads();
+    }
+
+    // bitonic sort of sel[0, kp_pad) into ranking order (score desc, row asc)
+    for (int ksz = 2; ksz <= kp_pad; ksz <<= 1) {
+        for (int j = ksz >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < kp_pad; i += blockDim.x) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const bool first_low = (i & ksz) == 0;
+                    const float s1 = sel_s[i], s2 = sel_s[p];
+                    const uint32_t r1 = sel_r[i], r2 = sel_r[p];
+                    const bool swap = first_low ? rr_before(s2, r2, s1, r1) : rr_before(s1, r1, s2, r2);
+                    if (swap) {
+                        sel_s[i] = s2;
+                        sel_r[i] = r2;
+                        sel_s[p] = s1;
+                        sel_r[p] = r1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+
+    bool pass = true;
+    if (RESCORE) {
+        const float bound = fmaxf(T, t_rest);
+        if (bound != RR_NEG_INF) {
+            // |bf16 score - exact score| <= eps for EVERY row:
+            //   (2^-8 + 2^-18) |q||x|   both operands rounded to bf16 (rel. 2^-9 each)
+            // + d_pad * 2^-22   |q||x|   fp32 accumulation slack in the tensor core
+            const double xn = (double)__uint_as_float(*a.max_norm_bits);
+            const double qn = (double)a.qnorm[qi];
+            const double eps = (3.90625e-3 + 3.814697265625e-6 + (double)a.d_pad * 2.384185791015625e-7) *
+                                   qn * xn * 1.00001 + 1e-30;
+            pass = (kp >= a.k) && sel_r[a.k - 1] != RR_NO_ROW &&
+                   ((double)sel_s[a.k - 1] > (double)bound + eps);
+        }
+    }
+    if (pass) {
+        for (int i = tid; i < a.k; i += blockDim.x) {
+            const bool ok = (i < kp) && sel_r[i] != RR_NO_ROW;
+            Dq[i] = ok ? sel_s[i] : -3.402823466e+38f;
+            Iq[i] = ok ? (int64_t)sel_r[i] + a.id_offset : (int64_t)-1;
+        }
+    } else if (tid == 0) {
+        a.fail_flags[qi] = 1;
+        a.fail_list[atomicAdd(&a.ctl->n_fail, 1)] = qi;
+        atomicAdd(a.nfail_total, 1);
+    }
+}
+
+// ------------------------------------------------------------------- host ---
+
+static int rr_grow(void** p, size_t* have, size_t want) {
+    if (*have >= want) return RR_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    size_t sz = want + want / 4;
+    cudaError_t e = cudaMalloc(p, sz);
+    if (e != cudaSuccess) {
+        e = cudaMalloc(p, want);
+        sz = want;
+    }
+    if (e != cudaSuccess) {
+        rr_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        cudaGetLastError();
+        return RR_ERR_OOM;
+    }
+    *have = sz;
+    return RR_OK;
+}
+
+extern "C" int rr_index_create(int d, int64_t capacity_rows, int device, rr_index_t** out) {
+    RR_REQUIRE(out != nullptr, "rr_index_create: out is NULL");
+    *out = nullptr;
+    RR_REQUIRE(d > 0 && d <= 65536, "rr_index_create: invalid dimension d=%d", d);
+    RR_REQUIRE(capacity_rows >= 0, "rr_index_create: negative capacity");
+    int rc = rr_check_device_arch(device);
+    if (rc != RR_OK) return rc;
+    rr_device_guard g(device);
+    rr_index* h = new (std::nothrow) rr_index();
+    RR_REQUIRE(h != nullptr, "rr_index_create: out of host memory");
+    h->d = d;
+    h->d_pad = (d + 63) / 64 * 64;
+    h->device = device;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        delete h;
+        rr_set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+        return RR_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    e = cudaMalloc(&h->max_norm_bits, 16);
+    if (e == cudaSuccess) e = cudaMemset(h->max_norm_bits, 0, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_nfail_total, 16);
+    if (e == cudaSuccess) e = cudaMemset(h->d_nfail_total, 0, 16);
+    if (e != cudaSuccess) {
+        rr_set_error("rr_index_create: %s", cudaGetErrorString(e));
+        rr_index_destroy(h);
+        return RR_ERR_CUDA;
+    }
+    if (capacity_rows > 0) {
+        rc = rr_index_reserve(h, capacity_rows);
+        if (rc != RR_OK) {
+            rr_index_destroy(h);
+            return rc;
+        }
+    }
+    *out = h;
+    return RR_OK;
+}
+
+extern "C" int rr_index_destroy(rr_index_t* h) {
+    if (!h) return RR_OK;
+    rr_device_guard g(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 64; ++i)
+        if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+    cudaFree(h->hi);
+    cudaFree(h->lo);
+    cudaFree(h->max_norm_bits);
+    cudaFree(h->d_nfail_total);
+    cudaFree(h->scratch);
+    cudaFree(h->stage);
+    delete h;
+    return RR_OK;
+}
+
+extern "C" int rr_index_reserve(rr_index_t* h, int64_t capacity_rows) {
+    RR_REQUIRE(h != nullptr, "rr_index_reserve: NULL handle");
+    if (capacity_rows <= h->cap) return RR_OK;
+    rr_device_guard g(h->device);
+    const size_t plane = (size_t)capacity_rows * h->d_pad * sizeof(uint16_t);
+    uint16_t *nhi = nullptr, *nlo = nullptr;
+    cudaError_t e = cudaMalloc(&nhi, plane);
+    if (e == cudaSuccess) e = cudaMalloc(&nlo, plane);
+    if (e != cudaSuccess) {
+        cudaFree(nhi);
+        cudaGetLastError();
+        rr_set_error("rr_index_reserve: cannot allocate 2 x %zu bytes for %lld rows: %s", plane,
+                     (long long)capacity_rows, cudaGetErrorString(e));
+        return RR_ERR_OOM;
+    }
+    if (h->n > 0) {
+        const size_t used = (size_t)h->n * h->d_pad * sizeof(uint16_t);
+        RR_CUDA_CHECK(cudaMemcpy(nhi, h->hi, used, cudaMemcpyDeviceToDevice));
+        RR_CUDA_CHECK(cudaMemcpy(nlo, h->lo, used, cudaMemcpyDeviceToDevice));
+    }
+    cudaFree(h->hi);
+    cudaFree(h->lo);
+    h->hi = nhi;
+    h->lo = nlo;
+    h->cap = capacity_rows;
+    h->tmap_hi_ptr = nullptr;
+    return RR_OK;
+}
+
+extern "C" int rr_index_add_f32(rr_index_t* h, const float* x, int64_t n, int x_on_device,
+                                void* stream_) {
+    RR_REQUIRE(h != nullptr, "rr_index_add_f32: NULL handle");
+    RR_REQUIRE(n >= 0, "rr_index_add_f32: negative n");
+    if (n == 0) return RR_OK;
+    RR_REQUIRE(x != nullptr, "rr_index_add_f32: x is NULL");
+    RR_REQUIRE(h->n + n <= 0xFFFFFFF0ll, "rr_index_add_f32: more than 2^32 rows in one shard");
+    rr_device_guard g(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (h->n + n > h->cap) {
+        // growing copies on the legacy stream: make prior async work visible first
+        RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        int64_t want = std::max<int64_t>(h->n + n, h->cap + h->cap / 2);
+        int rc = rr_index_reserve(h, want);
+        if (rc == RR_ERR_OOM && want > h->n + n) rc = rr_index_reserve(h, h->n + n);
+        if (rc != RR_OK) return rc;
+    }
+    const int blocks = h->sm_count * 8;
+    if (x_on_device) {
+        rr_split_rows_kernel<<<blocks, 256, 0, stream>>>(x, n, h->d, h->d_pad,
+                                                         h->hi + (size_t)h->n * h->d_pad,
+                                                         h->lo + (size_t)h->n * h->d_pad,
+                                                         h->max_norm_bits);
+        RR_CUDA_CHECK(cudaGetLastError());
+    } else {
+        const size_t row_bytes = (size_t)h->d * sizeof(float);
+        int64_t rows_per = std::max<int64_t>(1, (int64_t)((64u << 20) / row_bytes));
+        rows_per = std::min(rows_per, n);
+        int rc = rr_grow((void**)&h->stage, &h->stage_bytes, (size_t)rows_per * row_bytes);
+        if (rc != RR_OK) return rc;
+        for (int64_t r0 = 0; r0 < n; r0 += rows_per) {
+            const int64_t nr = std::min(rows_per, n - r0);
+            RR_CUDA_CHECK(cudaMemcpyAsync(h->stage, x + (size_t)r0 * h->d, (size_t)nr * row_bytes,
+                                          cudaMemcpyHostToDevice, stream));
+            rr_split_rows_kernel<<<blocks, 256, 0, stream>>>(
+                h->stage, nr, h->d, h->d_pad, h->hi + (size_t)(h->n + r0) * h->d_pad,
+                h->lo + (size_t)(h->n + r0) * h->d_pad, h->max_norm_bits);
+            RR_CUDA_CHECK(cudaGetLastError());
+            RR_CUDA_CHECK(cudaStreamSynchronize(stream));  // stage is reused
+        }
+    }
+    h->n += n;
+    return RR_OK;
+}
+
+extern "C" int rr_index_reset(rr_index_t* h) {
+    RR_REQUIRE(h != nullptr, "rr_index_reset: NULL handle");
+    rr_device_guard g(h->device);
+    RR_CUDA_CHECK(cudaDeviceSynchronize());
+    h->n = 0;
+    RR_CUDA_CHECK(cudaMemset(h->max_norm_bits, 0, 16));
+    return RR_OK;
+}
+
+extern "C" int64_t rr_index_ntotal(const rr_index_t* h) { return h ? h->n : -1; }
+extern "C" int rr_index_dim(const rr_index_t* h) { return h ? h->d : -1; }
+
+extern "C" int rr_index_reconstruct(rr_index_t* h, int64_t row0, int64_t n, float* out_dev,
+                                    void* stream) {
+    RR_REQUIRE(h != nullptr && out_dev != nullptr, "rr_index_reconstruct: NULL argument");
+    RR_REQUIRE(row0 >= 0 && n >= 0 && row0 + n <= h->n, "rr_index_reconstruct: rows [%lld, %lld) out of range (ntotal=%lld)",
+               (long long)row0, (long long)(row0 + n), (long long)h->n);
+    if (n == 0) return RR_OK;
+    rr_device_guard g(h->device);
+    rr_join_rows_kernel<<<h->sm_count * 8, 256, 0, (cudaStream_t)stream>>>(h->hi, h->lo, row0, n, h->d,
+                                                                          h->d_pad, out_dev);
+    RR_CUDA_CHECK(cudaGetLastError());
+    return RR_OK;
+}
+
+extern "C" int rr_index_set_id_offset(rr_index_t* h, int64_t offset) {
+    RR_REQUIRE(h != nullptr, "rr_index_set_id_offset: NULL handle");
+    h->id_offset = offset;
+    return RR_OK;
+}
+
+extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value) {
+    RR_REQUIRE(h != nullptr && name != nullptr, "rr_index_set_param: NULL argument");
+    if (!strcmp(name, "mode")) {
+        RR_REQUIRE(value == RR_MODE_AUTO || value == RR_MODE_EXACT, "mode must be 0 (auto) or 1 (exact)");
+        h->mode = (int)value;
+    } else if (!strcmp(name, "kprime")) {
+        RR_REQUIRE(value >= RR_MAX_K && value <= RR_FIN_MAXSEL, "kprime must be in [%d, %d]", RR_MAX_K, RR_FIN_MAXSEL);
+        h->kprime = (int)value;
+    } else if (!strcmp(name, "profile")) {
+        h->profile = value != 0;
+    } else {
+        rr_set_error("rr_index_set_param: unknown parameter '%s'", name);
+        return RR_ERR_INVALID;
+    }
+    return RR_OK;
+}
+
+static int rr_flush_events(rr_index* h) {
+    for (int i = 0; i + 1 < h->ev_used; i += 2) {
+        RR_CUDA_CHECK(cudaEventSynchronize(h->ev_pool[i + 1]));
+        float ms = 0.f;
+        RR_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
+        h->stats.scan_ms_total += ms;
+        h->stats.scan_launches += 1;
+        h->stats.scan_bytes_total += h->ev_bytes[i / 2];
+    }
+    h->ev_used = 0;
+    return RR_OK;
+}
+
+extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset) {
+    RR_REQUIRE(h != nullptr && out != nullptr, "rr_index_get_stats: NULL argument");
+    rr_device_guard g(h->device);
+    int rc = rr_flush_events(h);
+    if (rc != RR_OK) return rc;
+    int nf = 0;
+    RR_CUDA_CHECK(cudaMemcpy(&nf, h->d_nfail_total, sizeof(int), cudaMemcpyDeviceToHost));
+    h->stats.exact_rescans = nf;
+    *out = h->stats;
+    if (reset) {
+        h->stats.scan_ms_total = 0;
+        h->stats.scan_launches = 0;
+        h->stats.scan_bytes_total = 0;
+    }
+    return RR_OK;
+}
+
+static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// one chunk of <= RR_QCHUNK queries
+static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const uint8_t* mask_dev,
+                           int64_t mask_stride, float* D_dev, int64_t* I_dev, int64_t out_stride,
+                           cudaStream_t stream) {
+    const int qt = rr_tc_scan_qtile(h);  // 0: tc path unavailable for this d
+    const bool use_tc = (h->mode == RR_MODE_AUTO) && qt > 0 && h->n > 0;
+    const int nq_pad = (int)rr_align_up((size_t)nq, RR_TC_MAX_QTILE);
+    const int g_exact = h->sm_count * 2;
+    const int64_t cand_stride =
+        std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
+                          (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH);
+
+    // carve the scratch block
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = rr_align_up(off + bytes, 1024);
+        return o;
+    };
+    const size_t o_ctl = carve(sizeof(rr_chunk_ctl));
+    const size_t o_qbf = carve((size_t)nq_pad * h->d_pad * sizeof(uint16_t));
+    const size_t o_qn = carve((size_t)nq_pad * sizeof(float));
+    const size_t o_act = carve((size_t)nq_pad);
+    const size_t o_ff = carve((size_t)nq_pad);
+    const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
+    const size_t o_cs = carve((size_t)nq * cand_stride * sizeof(float));
+    const size_t o_cr = carve((size_t)nq * cand_stride * sizeof(uint32_t));
+    if (off > h->scratch_bytes) {
+        RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        int rc = rr_grow(&h->scratch, &h->scratch_bytes, off);
+        if (rc != RR_OK) return rc;
+    }
+    char* base = (char*)h->scratch;
+    rr_chunk_ctl* ctl = (rr_chunk_ctl*)(base + o_ctl);
+    uint16_t* qbf = (uint16_t*)(base + o_qbf);
+    float* qnorm = (float*)(base + o_qn);
+    uint8_t* active = (uint8_t*)(base + o_act);
+    uint8_t* fail_flags = (uint8_t*)(base + o_ff);
+    int* fail_list = (int*)(base + o_fl);
+    float* cand_s = (float*)(base + o_cs);
+    uint32_t* cand_r = (uint32_t*)(base + o_cr);
+
+    RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
+    rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, mask_dev, mask_stride,
+                                                       qbf, qnorm, active, fail_flags, fail_list, ctl,
+                                                       use_tc ? 0 : 1);
+    RR_CUDA_CHECK(cudaGetLastError());
+
+    rr_finalize_args fa;
+    fa.cand_s = cand_s;
+    fa.cand_r = cand_r;
+    fa.cand_stride = cand_stride;
+    fa.k = k;
+    fa.kprime = std::max(h->kprime, k);
+    fa.q = q_dev;
+    fa.qnorm = qnorm;
+    fa.hi = h->hi;
+    fa.lo = h->lo;
+    fa.d = h->d;
+    fa.d_pad = h->d_pad;
+    fa.max_norm_bits = h->max_norm_bits;
+    fa.id_offset = h->id_offset;
+    fa.D = D_dev;
+    fa.I = I_dev;
+    fa.out_stride = out_stride;
+    fa.active = active;
+    fa.fail_flags = fail_flags;
+    fa.fail_list = fail_list;
+    fa.ctl = ctl;
+    fa.nfail_total = h->d_nfail_total;
+    fa.pad_inactive = use_tc ? 0 : 1;
+
+    if (use_tc) {
+        for (int p0 = 0; p0 < nq; p0 += qt) {
+            const int nqt = std::min(qt, nq - p0);
+            int n_lists = 0;
+            const bool prof = h->profile != 0;
+            if (prof) {
+                if (h->ev_used + 2 > 64) {
+                    int rc = rr_flush_events(h);
+                    if (rc != RR_OK) return rc;
+                }
+                for (int i = 0; i < 2; ++i)
+                    if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
+                RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
+            }
+            int rc = rr_tc_scan_launch(h, qbf, nq_pad, p0, nqt, active + p0, &ctl->any_active,
+                                       cand_s + (size_t)p0 * cand_stride, cand_r + (size_t)p0 * cand_stride,
+                                       cand_stride, &n_lists, stream);
+            if (rc != RR_OK) return rc;
+            if (prof) {
+                RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
+                h->ev_bytes[h->ev_used / 2] = h->n * (int64_t)h->d_pad * 2;
+                h->ev_used += 2;
+            }
+            fa.n_lists = n_lists;
+            fa.depth = RR_TC_LIST_DEPTH;
+        }
+        rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
+        RR_CUDA_CHECK(cudaGetLastError());
+    }
+
+    // exact path over fail_list (everything when !use_tc); launches exit at once when empty
+    int qsub = RR_EXACT_MAX_QSUB;
+    while (qsub > 1 && (size_t)qsub * h->d_pad * sizeof(float) > (96u << 10)) qsub >>= 1;
+    const size_t ex_smem = (size_t)qsub * h->d_pad * sizeof(float) +
+                           (size_t)RR_EXACT_WARPS * qsub * RR_EXACT_LIST_DEPTH * 8 +
+                           (size_t)RR_EXACT_WARPS * qsub * sizeof(float) + (size_t)qsub * sizeof(int);
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_exact_scan_kernel<RR_EXACT_MAX_QSUB>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        attr_done[h->device & 63] = true;
+    }
+    RR_REQUIRE(ex_smem <= (200u << 10), "dimension %d too large for the exact scan kernel", h->d);
+    if (h->n > 0) {
+        for (int sub = 0; sub * qsub < nq; ++sub) {
+            rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<g_exact, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
+                h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, fail_list, ctl, sub, qsub, cand_s, cand_r,
+                cand_stride);
+            RR_CUDA_CHECK(cudaGetLastError());
+        }
+    }
+    fa.n_lists = (h->n > 0) ? g_exact : 0;
+    fa.depth = RR_EXACT_LIST_DEPTH;
+    rr_finalize_kernel<false><<<nq, RR_FIN_THREADS, 0, stream>>>(fa);
+    RR_CUDA_CHECK(cudaGetLastError());
+    return RR_OK;
+}
+
+extern "C" int rr_index_search_ex(rr_index_t* h, const float* q_dev, int64_t nq, int k,
+                                  const uint8_t* mask_dev, int64_t mask_stride, float* D_dev,
+                                  int64_t* I_dev, int64_t out_stride, void* stream_) {
+    RR_REQUIRE(h != nullptr, "rr_index_search: NULL handle");
+    RR_REQUIRE(nq >= 0, "rr_index_search: negative nq");
+    RR_REQUIRE(k > 0, "rr_index_search: k must be > 0 (got %d)", k);
+    if (k > RR_MAX_K) {
+        rr_set_error("rr_index_search: k=%d > RR_MAX_K=%d is not implemented", k, RR_MAX_K);
+        return RR_ERR_UNSUPPORTED;
+    }
+    if (nq == 0) return RR_OK;
+    RR_REQUIRE(q_dev && D_dev && I_dev, "rr_index_search: NULL buffer");
+    RR_REQUIRE(mask_dev == nullptr || mask_stride >= 1, "rr_index_search: bad mask stride");
+    if (out_stride == 0) out_stride = k;
+    RR_REQUIRE(out_stride >= k, "rr_index_search: out_stride < k");
+    rr_device_guard g(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    for (int64_t q0 = 0; q0 < nq; q0 += RR_QCHUNK) {
+        const int nqc = (int)std::min<int64_t>(RR_QCHUNK, nq - q0);
+        int rc = rr_search_chunk(h, q_dev + (size_t)q0 * h->d, nqc, k,
+                                 mask_dev ? mask_dev + q0 * mask_stride : nullptr, mask_stride,
+                                 D_dev + (size_t)q0 * out_stride, I_dev + (size_t)q0 * out_stride, out_stride,
+                                 stream);
+        if (rc != RR_OK) return rc;
+    }
+    h->stats.searches += 1;
+    h->stats.queries += nq;
+    return RR_OK;
+}
+
+extern "C" int rr_index_search_masked(rr_index_t* h, const float* q_dev, int64_t nq, int k,
+                                      const uint8_t* mask_dev, int64_t mask_stride, float* D_dev,
+                                      int64_t* I_dev, void* stream) {
+    return rr_index_search_ex(h, q_dev, nq, k, mask_dev, mask_stride, D_dev, I_dev, 0, stream);
+}
+
+extern "C" int rr_index_search(rr_index_t* h, const float* q_dev, int64_t nq, int k, float* D_dev,
+                               int64_t* I_dev, void* stream) {
+    return rr_index_search_ex(h, q_dev, nq, k, nullptr, 0, D_dev, I_dev, 0, stream);
+}
+
+extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t nq, int k,
+                                    float* D_host, int64_t* I_host) {
+    RR_REQUIRE(h != nullptr, "rr_index_search_host: NULL handle");
+    RR_REQUIRE(nq >= 0 && k > 0, "rr_index_search_host: bad nq / k");
+    if (nq == 0) return RR_OK;
+    RR_REQUIRE(q_host && D_host && I_host, "rr_index_search_host: NULL buffer");
+    rr_device_guard g(h->device);
+    const size_t qb = rr_align_up((size_t)nq * h->d * sizeof(float), 256);
+    const size_t db = rr_align_up((size_t)nq * k * sizeof(float), 256);
+    const size_t ib = (size_t)nq * k * sizeof(int64_t);
+    int rc = rr_grow((void**)&h->stage, &h->stage_bytes, qb + db + ib);
+    if (rc != RR_OK) return rc;
+    char* base = (char*)h->stage;
+    float* q_dev = (float*)base;
+    float* D_dev = (float*)(base + qb);
+    int64_t* I_dev = (int64_t*)(base + qb + db);
+    cudaStream_t stream = 0;
+    RR_CUDA_CHECK(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, stream));
+    rc = rr_index_search(h, q_dev, nq, k, D_dev, I_dev, stream);
+    if (rc != RR_OK) return rc;
+    RR_CUDA_CHECK(cudaMemcpyAsync(D_host, D_dev, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    RR_CUDA_CHECK(cudaMemcpyAsync(I_host, I_dev, ib, cudaMemcpyDeviceToHost, stream));
+    RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return RR_OK;
+}
+
+extern "C" int rr_index_tc_qtile(const rr_index_t* h) { return h ? rr_tc_scan_qtile(h) : RR_ERR_INVALID; }
+
+extern "C" int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq, float* cand_s_dev,
+                                      uint32_t* cand_r_dev, int64_t capacity, int* n_lists, int* depth,
+                                      void* stream_) {
+    RR_REQUIRE(h && q_dev && cand_s_dev && cand_r_dev && n_lists && depth, "rr_index_debug_tc_scan: NULL argument");
+    const int qt = rr_tc_scan_qtile(h);
+    RR_REQUIRE(qt > 0 && nq >= 1 && nq <= qt, "rr_index_debug_tc_scan: nq must be in [1, %d]", qt);
+    RR_REQUIRE(h->n > 0, "rr_index_debug_tc_scan: empty index");
+    rr_device_guard g(h->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int64_t stride = (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH;
+    RR_REQUIRE(capacity >= stride, "rr_index_debug_tc_scan: capacity %lld < %lld entries per query",
+               (long long)capacity, (long long)stride);
+    size_t off = 0;
+    auto carve = [&](size_t bytes) {
+        size_t o = off;
+        off = rr_align_up(off + bytes, 1024);
+        return o;
+    };
+    const int nq_pad = RR_TC_MAX_QTILE;
+    const size_t o_ctl = carve(sizeof(rr_chunk_ctl));
+    const size_t o_qbf = carve((size_t)nq_pad * h->d_pad * sizeof(uint16_t));
+    const size_t o_qn = carve((size_t)nq_pad * sizeof(float));
+    const size_t o_act = carve((size_t)nq_pad);
+    const size_t o_ff = carve((size_t)nq_pad);
+    const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
+    if (off > h->scratch_bytes) {
+        RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+        int rc = rr_grow(&h->scratch, &h->scratch_bytes, off);
+        if (rc != RR_OK) return rc;
+    }
+    char* base = (char*)h->scratch;
+    rr_chunk_ctl* ctl = (rr_chunk_ctl*)(base + o_ctl);
+    RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
+    rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, nullptr, 0,
+                                                       (uint16_t*)(base + o_qbf), (float*)(base + o_qn),
+                                                       (uint8_t*)(base + o_act), (uint8_t*)(base + o_ff),
+                                                       (int*)(base + o_fl), ctl, 0);
+    RR_CUDA_CHECK(cudaGetLastError());
+    RR_CUDA_CHECK(cudaMemsetAsync(cand_s_dev, 0xFF, (size_t)nq * capacity * sizeof(float), stream));
+    RR_CUDA_CHECK(cudaMemsetAsync(cand_r_dev, 0xFF, (size_t)nq * capacity * sizeof(uint32_t), stream));
+    int rc = rr_tc_scan_launch(h, (uint16_t*)(base + o_qbf), nq_pad, 0, nq, (uint8_t*)(base + o_act),
+                               &ctl->any_active, cand_s_dev, cand_r_dev, capacity, n_lists, stream);
+    if (rc != RR_OK) return rc;
+    *depth = RR_TC_LIST_DEPTH;
+    return RR_OK;
+}
+
+extern "C" int rr_normalize_l2(float* x_dev, int64_t n, int d, void* stream) {
+    RR_REQUIRE(n >= 0 && d > 0, "rr_normalize_l2: bad shape");
+    if (n == 0) return RR_OK;
+    RR_REQUIRE(x_dev != nullptr, "rr_normalize_l2: NULL buffer");
+    RR_REQUIRE(n <= 0x7FFFFFFF, "rr_normalize_l2: too many rows");
+    rr_normalize_l2_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(x_dev, n, d);
+    RR_CUDA_CHECK(cudaGetLastError());
+    return RR_OK;
+}

@@ -1,0 +1,68 @@
+// Internal layout of an index handle, shared by rr_index.cu and rr_scan_tc.cu.
+#pragma once
+#include "rr_common.cuh"
+
+// Candidate lists produced by a scan kernel for one chunk of queries:
+//   cand_s / cand_r : [n_queries][n_lists][depth]   (score fp32, local row u32)
+// Each list is sorted (score desc, row asc); empty slots are (-inf, RR_NO_ROW).
+// A list whose last slot is occupied may have dropped rows, all of which score
+// <= that last slot.
+
+constexpr int RR_TC_TILE_ROWS = 128;   // corpus rows per MMA tile (UMMA M)
+constexpr int RR_TC_KCHUNK = 64;       // bf16 elements per 128-byte swizzle row
+constexpr int RR_TC_MAX_QTILE = 64;    // queries per scan pass (UMMA N <= 64)
+constexpr int RR_TC_LIST_DEPTH = 16;   // entries per (epilogue warp, query) list
+constexpr int RR_TC_EPI_WARPS = 4;
+constexpr int RR_EXACT_LIST_DEPTH = 32;
+constexpr int RR_EXACT_WARPS = 8;
+constexpr int RR_QCHUNK = 256;         // queries handled per internal chunk
+constexpr int RR_EXACT_MAX_QSUB = 16;  // queries per exact-scan launch
+
+struct rr_index {
+    int d = 0;
+    int d_pad = 0;  // d rounded up to a multiple of 64 (zero padded)
+    int device = 0;
+    int sm_count = 0;
+    int64_t n = 0;
+    int64_t cap = 0;
+    int64_t id_offset = 0;
+    uint16_t* hi = nullptr;  // [cap, d_pad] bf16 plane (MMA operand)
+    uint16_t* lo = nullptr;  // [cap, d_pad] remainder plane
+    uint32_t* max_norm_bits = nullptr;  // device: max row L2 norm (as float bits)
+
+    // parameters
+    int mode = RR_MODE_AUTO;
+    int kprime = 128;
+    int profile = 0;
+
+    // per-search scratch (grow-only)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    float* stage = nullptr;  // host->device staging for add / search_host
+    size_t stage_bytes = 0;
+
+    // TMA descriptor of the hi plane (rebuilt when hi / n change)
+    alignas(64) CUtensorMap tmap_hi;
+    const void* tmap_hi_ptr = nullptr;
+    int64_t tmap_hi_rows = -1;
+
+    // stats
+    rr_index_stats stats = {};
+    int* d_nfail_total = nullptr;  // device counter of certificate failures
+    cudaEvent_t ev_pool[64] = {};
+    int ev_used = 0;
+    int64_t ev_bytes[32] = {};
+};
+
+// rr_scan_tc.cu: launch the tcgen05 scan for one pass of <= qtile queries: rows
+// [q_row0, q_row0 + qtile) of the bf16 query buffer qbf16 [q_rows_total, d_pad]
+// (zero padded), of which the first nq_tile are real.  active [nq_tile] uint8:
+// 0 = query not routed to this source.  Fills cand_s / cand_r (already offset to
+// the pass's first query) and reports the number of lists per query.
+int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
+                      const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
+                      int64_t cand_stride, int* n_lists_out, cudaStream_t stream);
+// number of candidate lists per query the tc scan produces for this index
+int rr_tc_scan_num_lists(const rr_index* h);
+// queries per pass for this dimension (stationary query tile must fit in smem)
+int rr_tc_scan_qtile(const rr_index* h);

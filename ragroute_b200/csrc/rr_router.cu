@@ -1,0 +1,398 @@
+// B2: router relevance MLP (/root/reference/ragroute/router.py:37-55 CorpusRoutingNN,
+// :241-283 select_relevant_sources_ragroute) as ONE kernel: feature scaling, fc1,
+// LayerNorm, ReLU, fc2, LayerNorm, ReLU, fc3, sigmoid and threshold for every
+// (query, source) pair of a batch, nothing but the mask / logits written to HBM.
+//
+// The feature row of a pair is [pad(q) | centroid_s | onehot_s] (router.py:253-265);
+// only the first d_max columns depend on the query, so fc1 splits into
+//   W1[:, :d_max] . xq           shared by all sources that use the same encoder
+// + c1_s = b1 + W1[:, d_max:] . xconst_s   folded once per source at load time.
+// The scaler is applied exactly as the reference does: (x - mean_) / scale_ in
+// float64, then cast to fp32 (router.py:270-271).
+#include <math.h>
+
+#include <new>
+#include <vector>
+
+#include "rr_common.cuh"
+
+namespace {
+constexpr int kH1 = 256;
+constexpr int kH2 = 128;
+constexpr int kQB = 4;         // queries (or rows) per CTA
+constexpr int kThreads = 512;  // 2 K-halves x 256 fc1 outputs; 16 warps for the pair phase
+constexpr int kWarps = kThreads / 32;
+constexpr float kLnEps = 1e-5f;
+}  // namespace
+
+struct rr_router {
+    int device = 0;
+    int in_dim = 0;
+    // device weights
+    float* w1t = nullptr;  // [in_dim][256]  (fc1.weight transposed)
+    float* b1 = nullptr;
+    float* ln1w = nullptr;
+    float* ln1b = nullptr;
+    float* w2t = nullptr;  // [256][128]
+    float* b2 = nullptr;
+    float* ln2w = nullptr;
+    float* ln2b = nullptr;
+    float* w3 = nullptr;  // [128]
+    float* b3 = nullptr;  // [1]
+    std::vector<float> h_w1;  // host copy of fc1.weight [256][in_dim] for table folding
+    std::vector<float> h_b1;
+    // select tables
+    int n_sources = 0, d_max = 0, n_slots = 0;
+    int* slot_of_source = nullptr;  // device [S]
+    float* c1 = nullptr;            // device [S][256]
+    double* sc_mean = nullptr;      // device [d_max] or null
+    double* sc_scale = nullptr;
+};
+
+namespace {
+
+struct RouterArgs {
+    const float* w1t;
+    const float* ln1w;
+    const float* ln1b;
+    const float* w2t;
+    const float* b2;
+    const float* ln2w;
+    const float* ln2b;
+    const float* w3;
+    const float* b3;
+    const float* c1;          // [S][256] per-source fc1 constant (logits mode: b1, S = 1)
+    const int* slot_of_source;  // [S] or null (all 0)
+    const double* sc_mean;    // [d_in] or null
+    const double* sc_scale;
+    const float* x;           // [B][n_slots][d_in]
+    int64_t B;
+    int S;
+    int n_slots;
+    int d_in;                 // columns of x consumed by fc1 (d_max, or in_dim in logits mode)
+    float prob_thr;
+    uint8_t* mask;            // [B][S] or null
+    float* logits;            // [B][S] or null
+};
+
+__global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    float* xq = sm;                                 // [kQB][d_in]
+    float* part = xq + (size_t)kQB * a.d_in;        // [2][kQB][256]
+    float* g = part + 2 * kQB * kH1;                // [n_slots][kQB][256]
+    float* hbuf = g + (size_t)a.n_slots * kQB * kH1;  // [kWarps][256]
+
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t b0 = (int64_t)blockIdx.x * kQB;
+    const int nqb = (int)min((int64_t)kQB, a.B - b0);
+
+    // ---- phase 1: g[slot][qb][:] = W1[:, :d_in] . scaled(x[qb][slot][:]) ----
+    const int t = tid & (kH1 - 1);
+    const int half = tid >> 8;
+    const int j_lo = half ? (a.d_in >> 1) : 0;
+    const int j_hi = half ? a.d_in : (a.d_in >> 1);
+    for (int sl = 0; sl < a.n_slots; ++sl) {
+        for (int i = tid; i < kQB * a.d_in; i += kThreads) {
+            const int qb = i / a.d_in, j = i - qb * a.d_in;
+            float v = 0.f;
+            if (qb < nqb) {
+                v = a.x[((b0 + qb) * a.n_slots + sl) * (int64_t)a.d_in + j];
+                if (a.sc_mean) v = (float)(((double)v - a.sc_mean[j]) / a.sc_scale[j]);
+            }
+            xq[i] = v;
+        }
+        __syncthreads();
+        float acc[kQB];
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) acc[qb] = 0.f;
+        const float* wp = a.w1t + t;
+        int j = j_lo;
+        for (; j + 4 <= j_hi; j += 4) {
+            const float w0 = __ldg(wp + (size_t)(j + 0) * kH1);
+            const float w1 = __ldg(wp + (size_t)(j + 1) * kH1);
+            const float w2 = __ldg(wp + (size_t)(j + 2) * kH1);
+            const float w3 = __ldg(wp + (size_t)(j + 3) * kH1);
+#pragma unroll
+            for (int qb = 0; qb < kQB; ++qb) {
+                const float* xr = xq + (size_t)qb * a.d_in + j;
+                acc[qb] = fmaf(w0, xr[0], acc[qb]);
+                acc[qb] = fmaf(w1, xr[1], acc[qb]);
+                acc[qb] = fmaf(w2, xr[2], acc[qb]);
+                acc[qb] = fmaf(w3, xr[3], acc[qb]);
+            }
+        }
+        for (; j < j_hi; ++j) {
+            const float w0 = __ldg(wp + (size_t)j * kH1);
+#pragma unroll
+            for (int qb = 0; qb < kQB; ++qb) acc[qb] = fmaf(w0, xq[(size_t)qb * a.d_in + j], acc[qb]);
+        }
+#pragma unroll
+        for (int qb = 0; qb < kQB; ++qb) part[(half * kQB + qb) * kH1 + t] = acc[qb];
+        __syncthreads();
+        for (int i = tid; i < kQB * kH1; i += kThreads)
+            g[(size_t)sl * kQB * kH1 + i] = part[i] + part[kQB * kH1 + i];
+        __syncthreads();
+    }
+
+    // ---- phase 2: one warp per (query, source) pair ----
+    float* hw = hbuf + w * kH1;
+    const int n_pairs = nqb * a.S;
+    for (int pi = w; pi < n_pairs; pi += kWarps) {
+        const int qb = pi / a.S, s = pi - qb * a.S;
+        const int sl = a.slot_of_source ? a.slot_of_source[s] : 0;
+        const float* gp = g + ((size_t)sl * kQB + qb) * kH1;
+        const float* cp = a.c1 + (size_t)s * kH1;
+        float h[8];
+        float sum = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = lane + 32 * c;
+            h[c] = gp[i] + cp[i];
+            sum += h[c];
+        }
+        const float mean1 = rr_warp_sum(sum) * (1.0f / kH1);
+        float var = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const float dlt = h[c] - mean1;
+            var = fmaf(dlt, dlt, var);
+        }
+        const float rstd1 = 1.0f / sqrtf(rr_warp_sum(var) * (1.0f / kH1) + kLnEps);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int i = lane + 32 * c;
+            const float y = (h[c] - mean1) * rstd1 * a.ln1w[i] + a.ln1b[i];
+            hw[i] = fmaxf(y, 0.f);
+        }
+        __syncwarp();
+        float o[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[c] = a.b2[lane + 32 * c];
+        for (int i = 0; i < kH1; ++i) {
+            const float hv = hw[i];
+            const float* wr = a.w2t + (size_t)i * kH2 + lane;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[c] = fmaf(__ldg(wr + 32 * c), hv, o[c]);
+        }
+        float sum2 = o[0] + o[1] + o[2] + o[3];
+        const float mean2 = rr_warp_sum(sum2) * (1.0f / kH2);
+        float var2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const float dlt = o[c] - mean2;
+            var2 = fmaf(dlt, dlt, var2);
+        }
+        const float rstd2 = 1.0f / sqrtf(rr_warp_sum(var2) * (1.0f / kH2) + kLnEps);
+        float dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int i = lane + 32 * c;
+            const float y = fmaxf((o[c] - mean2) * rstd2 * a.ln2w[i] + a.ln2b[i], 0.f);
+            dot = fmaf(a.w3[i], y, dot);
+        }
+        const float logit = rr_warp_sum(dot) + a.b3[0];
+        if (lane == 0) {
+            const int64_t oidx = (b0 + qb) * a.S + s;
+            if (a.logits) a.logits[oidx] = logit;
+            if (a.mask) {
+                const float prob = 1.0f / (1.0f + expf(-logit));  // torch.sigmoid, router.py:276
+                a.mask[oidx] = prob > a.prob_thr ? 1 : 0;          // strict, router.py:278-280
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <typename T>
+int upload(T** dst, const T* src, size_t n) {
+    RR_CUDA_CHECK(cudaMalloc((void**)dst, n * sizeof(T)));
+    RR_CUDA_CHECK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return RR_OK;
+}
+
+size_t router_smem(int d_in, int n_slots) {
+    return ((size_t)kQB * d_in + 2 * kQB * kH1 + (size_t)n_slots * kQB * kH1 + (size_t)kWarps * kH1) *
+           sizeof(float);
+}
+
+int router_launch(rr_router* h, const RouterArgs& a, cudaStream_t stream) {
+    const size_t smem = router_smem(a.d_in, a.n_slots);
+    RR_REQUIRE(smem <= (size_t)227 * 1024, "router: %zu bytes of shared memory needed (d_in=%d, slots=%d)",
+               smem, a.d_in, a.n_slots);
+    RR_CUDA_CHECK(cudaFuncSetAttribute(rr_router_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+    const unsigned blocks = (unsigned)((a.B + kQB - 1) / kQB);
+    rr_router_kernel<<<blocks, kThreads, smem, stream>>>(a);
+    RR_CUDA_CHECK(cudaGetLastError());
+    (void)h;
+    return RR_OK;
+}
+
+RouterArgs base_args(const rr_router* h) {
+    RouterArgs a = {};
+    a.w1t = h->w1t;
+    a.ln1w = h->ln1w;
+    a.ln1b = h->ln1b;
+    a.w2t = h->w2t;
+    a.b2 = h->b2;
+    a.ln2w = h->ln2w;
+    a.ln2b = h->ln2b;
+    a.w3 = h->w3;
+    a.b3 = h->b3;
+    return a;
+}
+
+}  // namespace
+
+extern "C" int rr_router_create(int in_dim, int h1, int h2, const float* fc1_w, const float* fc1_b,
+                                const float* ln1_w, const float* ln1_b, const float* fc2_w,
+                                const float* fc2_b, const float* ln2_w, const float* ln2_b,
+                                const float* fc3_w, const float* fc3_b, int device, rr_router_t** out) {
+    RR_REQUIRE(out != nullptr, "rr_router_create: out is NULL");
+    *out = nullptr;
+    RR_REQUIRE(in_dim > 0, "rr_router_create: in_dim must be positive");
+    if (h1 != kH1 || h2 != kH2) {
+        rr_set_error("rr_router_create: hidden sizes %d/%d; CorpusRoutingNN is 256/128 (router.py:40,44)", h1, h2);
+        return RR_ERR_UNSUPPORTED;
+    }
+    RR_REQUIRE(fc1_w && fc1_b && ln1_w && ln1_b && fc2_w && fc2_b && ln2_w && ln2_b && fc3_w && fc3_b,
+               "rr_router_create: NULL weight pointer");
+    int rc = rr_check_device_arch(device);
+    if (rc != RR_OK) return rc;
+    rr_device_guard g(device);
+    rr_router* h = new (std::nothrow) rr_router();
+    RR_REQUIRE(h != nullptr, "rr_router_create: out of host memory");
+    h->device = device;
+    h->in_dim = in_dim;
+    h->h_w1.assign(fc1_w, fc1_w + (size_t)kH1 * in_dim);
+    h->h_b1.assign(fc1_b, fc1_b + kH1);
+    std::vector<float> w1t((size_t)in_dim * kH1), w2t((size_t)kH1 * kH2);
+    for (int o = 0; o < kH1; ++o)
+        for (int j = 0; j < in_dim; ++j) w1t[(size_t)j * kH1 + o] = fc1_w[(size_t)o * in_dim + j];
+    for (int o = 0; o < kH2; ++o)
+        for (int j = 0; j < kH1; ++j) w2t[(size_t)j * kH2 + o] = fc2_w[(size_t)o * kH1 + j];
+    rc = upload(&h->w1t, w1t.data(), w1t.size());
+    if (rc == RR_OK) rc = upload(&h->b1, fc1_b, kH1);
+    if (rc == RR_OK) rc = upload(&h->ln1w, ln1_w, kH1);
+    if (rc == RR_OK) rc = upload(&h->ln1b, ln1_b, kH1);
+    if (rc == RR_OK) rc = upload(&h->w2t, w2t.data(), w2t.size());
+    if (rc == RR_OK) rc = upload(&h->b2, fc2_b, kH2);
+    if (rc == RR_OK) rc = upload(&h->ln2w, ln2_w, kH2);
+    if (rc == RR_OK) rc = upload(&h->ln2b, ln2_b, kH2);
+    if (rc == RR_OK) rc = upload(&h->w3, fc3_w, kH2);
+    if (rc == RR_OK) rc = upload(&h->b3, fc3_b, 1);
+    if (rc != RR_OK) {
+        rr_router_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return RR_OK;
+}
+
+extern "C" int rr_router_destroy(rr_router_t* h) {
+    if (!h) return RR_OK;
+    rr_device_guard g(h->device);
+    cudaDeviceSynchronize();
+    float* fs[] = {h->w1t, h->b1, h->ln1w, h->ln1b, h->w2t, h->b2, h->ln2w, h->ln2b, h->w3, h->b3, h->c1};
+    for (float* p : fs) cudaFree(p);
+    cudaFree(h->slot_of_source);
+    cudaFree(h->sc_mean);
+    cudaFree(h->sc_scale);
+    delete h;
+    return RR_OK;
+}
+
+extern "C" int rr_router_logits(rr_router_t* h, const float* x_dev, int64_t P, float* logits_dev,
+                                void* stream) {
+    RR_REQUIRE(h != nullptr, "rr_router_logits: NULL handle");
+    RR_REQUIRE(P >= 0, "rr_router_logits: negative P");
+    if (P == 0) return RR_OK;
+    RR_REQUIRE(x_dev && logits_dev, "rr_router_logits: NULL buffer");
+    rr_device_guard g(h->device);
+    RouterArgs a = base_args(h);
+    a.c1 = h->b1;
+    a.x = x_dev;
+    a.B = P;
+    a.S = 1;
+    a.n_slots = 1;
+    a.d_in = h->in_dim;
+    a.logits = logits_dev;
+    return router_launch(h, a, (cudaStream_t)stream);
+}
+
+extern "C" int rr_router_set_tables(rr_router_t* h, int n_sources, int d_max, int n_slots,
+                                    const int32_t* slot_of_source, const float* centroids,
+                                    const int32_t* onehot_id, int n_onehot, const double* scaler_mean,
+                                    const double* scaler_scale) {
+    RR_REQUIRE(h != nullptr, "rr_router_set_tables: NULL handle");
+    RR_REQUIRE(n_sources > 0 && d_max > 0 && n_slots > 0 && n_onehot >= 0, "rr_router_set_tables: bad sizes");
+    RR_REQUIRE(2 * d_max + n_onehot == h->in_dim,
+               "rr_router_set_tables: 2*d_max + n_onehot = %d but the network's in_dim is %d",
+               2 * d_max + n_onehot, h->in_dim);
+    RR_REQUIRE(slot_of_source && centroids && (n_onehot == 0 || onehot_id), "rr_router_set_tables: NULL table");
+    RR_REQUIRE((scaler_mean == nullptr) == (scaler_scale == nullptr), "rr_router_set_tables: scaler needs mean and scale");
+    for (int s = 0; s < n_sources; ++s) {
+        RR_REQUIRE(slot_of_source[s] >= 0 && slot_of_source[s] < n_slots, "rr_router_set_tables: slot out of range");
+        RR_REQUIRE(n_onehot == 0 || (onehot_id[s] >= 0 && onehot_id[s] < n_onehot), "rr_router_set_tables: one-hot id out of range");
+    }
+    rr_device_guard g(h->device);
+    RR_CUDA_CHECK(cudaDeviceSynchronize());
+    const int in_dim = h->in_dim;
+    // c1_s = b1 + W1[:, d_max:] . fp32(scaled [centroid_s | onehot_s])   (float64 accumulate)
+    std::vector<float> c1((size_t)n_sources * kH1);
+    std::vector<float> xc(in_dim - d_max);
+    for (int s = 0; s < n_sources; ++s) {
+        for (int j = 0; j < in_dim - d_max; ++j) {
+            double f = (j < d_max) ? (double)centroids[(size_t)s * d_max + j]
+                                   : ((j - d_max) == onehot_id[s] ? 1.0 : 0.0);
+            if (scaler_mean) f = (f - scaler_mean[d_max + j]) / scaler_scale[d_max + j];
+            xc[j] = (float)f;  // the reference casts the scaled row to fp32 (router.py:271)
+        }
+        for (int o = 0; o < kH1; ++o) {
+            double acc = (double)h->h_b1[o];
+            const float* wr = h->h_w1.data() + (size_t)o * in_dim + d_max;
+            for (int j = 0; j < in_dim - d_max; ++j) acc += (double)wr[j] * (double)xc[j];
+            c1[(size_t)s * kH1 + o] = (float)acc;
+        }
+    }
+    cudaFree(h->c1);
+    cudaFree(h->slot_of_source);
+    cudaFree(h->sc_mean);
+    cudaFree(h->sc_scale);
+    h->c1 = nullptr;
+    h->slot_of_source = nullptr;
+    h->sc_mean = h->sc_scale = nullptr;
+    int rc = upload(&h->c1, c1.data(), c1.size());
+    if (rc == RR_OK) rc = upload(&h->slot_of_source, slot_of_source, (size_t)n_sources);
+    if (rc == RR_OK && scaler_mean) rc = upload(&h->sc_mean, scaler_mean, (size_t)d_max);
+    if (rc == RR_OK && scaler_scale) rc = upload(&h->sc_scale, scaler_scale, (size_t)d_max);
+    if (rc != RR_OK) return rc;
+    h->n_sources = n_sources;
+    h->d_max = d_max;
+    h->n_slots = n_slots;
+    return RR_OK;
+}
+
+extern "C" int rr_router_select(rr_router_t* h, const float* q_dev, int64_t B, float prob_threshold,
+                                uint8_t* mask_dev, float* logits_dev, void* stream) {
+    RR_REQUIRE(h != nullptr, "rr_router_select: NULL handle");
+    RR_REQUIRE(h->n_sources > 0, "rr_router_select: call rr_router_set_tables first");
+    RR_REQUIRE(B >= 0, "rr_router_select: negative B");
+    if (B == 0) return RR_OK;
+    RR_REQUIRE(q_dev && (mask_dev || logits_dev), "rr_router_select: NULL buffer");
+    rr_device_guard g(h->device);
+    RouterArgs a = base_args(h);
+    a.c1 = h->c1;
+    a.slot_of_source = h->slot_of_source;
+    a.sc_mean = h->sc_mean;
+    a.sc_scale = h->sc_scale;
+    a.x = q_dev;
+    a.B = B;
+    a.S = h->n_sources;
+    a.n_slots = h->n_slots;
+    a.d_in = h->d_max;
+    a.prob_thr = prob_threshold;
+    a.mask = mask_dev;
+    a.logits = logits_dev;
+    return router_launch(h, a, (cudaStream_t)stream);
+}

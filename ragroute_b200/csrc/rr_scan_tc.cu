@@ -1,0 +1,496 @@
+// The scoring pass: scores = X_bf16 . Q_bf16^T on tcgen05 tensor cores with the
+// per-query top-M selection fused into the TMEM epilogue, so no [B, N] score
+// matrix is ever written.  Replaces the arithmetic of faiss IndexFlatIP::search
+// (/root/reference/ragroute/data_source.py:158,186,203) up to the exact rescoring
+// done in rr_index.cu.
+//
+// Shape of the problem at B <= 64: arithmetic intensity = B flop/byte over the
+// bf16 plane, far below the ridge (~215), so the kernel is built around the HBM
+// stream, not around MMA throughput:
+//   * corpus rows are the UMMA M operand (128 rows x 64 k per stage, 16 KB, TMA,
+//     128B swizzle), so even one query fills the tensor core ("swap-AB");
+//   * the query tile (<= 64 x d bf16) is the UMMA N operand and stays resident in
+//     shared memory for the whole kernel (loaded once by TMA);
+//   * a ring of 4-8 corpus stages keeps >= 64 KB in flight per SM;
+//   * persistent grid of one CTA per SM, tiles round-robin so neighbouring SMs
+//     stream neighbouring rows;
+//   * accumulators: 4 TMEM stages of QT fp32 columns; the epilogue of tile i runs
+//     under the MMAs of tiles i+1..i+3.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = epilogue
+// (each owns the 32 TMEM lanes = 32 corpus rows of its quadrant and keeps, per
+// query, a sorted top-16 list in shared memory; see rr_topm.cuh).
+#include <algorithm>
+
+#include "rr_index_internal.cuh"
+#include "rr_topm.cuh"
+
+namespace {
+
+constexpr int kStageBytes = RR_TC_TILE_ROWS * RR_TC_KCHUNK * 2;  // 16 KB
+constexpr int kAccStages = 4;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kDepth = RR_TC_LIST_DEPTH;
+constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+
+struct TcParams {
+    int64_t n_rows;
+    int n_tiles;
+    int num_kc;   // d_pad / 64
+    int nq_tile;  // valid queries in this pass (<= QT)
+    int q_row0;   // first row of the pass inside the query buffer
+    int stages;
+    const uint8_t* active;   // [nq_tile]
+    const int* any_active;   // device flag: 0 -> nothing routed here, exit at once
+    float* cand_s;           // [query][list][kDepth]
+    uint32_t* cand_r;
+    int64_t cand_stride;
+};
+
+// ------------------------------------------------------------- PTX wrappers --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok;
+}
+// Bounded wait: a pipeline-protocol bug must trap (reported as a CUDA error), never
+// hang the device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s at 2 GHz
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
+                                            int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        :
+        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, K-major operand, 128B swizzle, rows of 128 bytes,
+// 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14),
+// LBO>>4 [16,30) = 1 (unused with swizzle), SBO>>4 [32,46) = 64, version [46,48) = 1,
+// layout_type [61,64) = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4,
+// a_format BF16 = 1 @7, b_format BF16 = 1 @10, a/b K-major (bits 15,16 = 0),
+// N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Candidate handling for one (epilogue warp, query): `b` = lanes whose score beats
+// the list's current tail.  Kept out of line: it runs for a small fraction of the
+// (tile, query) pairs.
+__device__ __noinline__ void epi_take(float v, unsigned b, uint32_t row, float* ls_q, uint32_t* lr_q,
+                                      float* thr_q, int lane) {
+    float es = RR_NEG_INF;
+    uint32_t er = RR_NO_ROW;
+    if (lane < kDepth) {
+        es = ls_q[lane];
+        er = lr_q[lane];
+    }
+    if (__popc(b) <= 3) {
+        while (b) {
+            const int src = __ffs(b) - 1;
+            b &= b - 1;
+            const float cv = __shfl_sync(RR_FULL, v, src);
+            const uint32_t cr = __shfl_sync(RR_FULL, row, src);
+            rr_list_insert(es, er, cv, cr, kDepth, lane);
+        }
+    } else {
+        float cs = ((b >> lane) & 1u) ? v : RR_NEG_INF;
+        uint32_t cr = ((b >> lane) & 1u) ? row : RR_NO_ROW;
+        rr_warp_sort(cs, cr, lane);
+        rr_list_merge_sorted(es, er, cs, cr, kDepth, lane);
+    }
+    if (lane < kDepth) {
+        ls_q[lane] = es;
+        lr_q[lane] = er;
+    }
+    const float tail = __shfl_sync(RR_FULL, es, kDepth - 1);
+    const uint32_t tail_r = __shfl_sync(RR_FULL, er, kDepth - 1);
+    if (lane == 0) *thr_q = (tail_r != RR_NO_ROW) ? tail : RR_NEG_INF;
+    __syncwarp();
+}
+
+template <int QT>
+__global__ void __launch_bounds__(kThreads, 1)
+rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
+                  const TcParams p) {
+    if (*p.any_active == 0) return;  // no query routed to this source: do not touch the corpus
+
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    // carve (all offsets multiples of 1024 for the swizzled tiles)
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                               ~(uintptr_t)1023);
+    const int q_bytes = p.num_kc * QT * 128;
+    uint8_t* q_sm = base;
+    uint8_t* x_sm = base + q_bytes;
+    float* ls = reinterpret_cast<float*>(x_sm + p.stages * kStageBytes);      // [4][QT][kDepth]
+    uint32_t* lr = reinterpret_cast<uint32_t*>(ls + RR_TC_EPI_WARPS * QT * kDepth);
+    float* thr = reinterpret_cast<float*>(lr + RR_TC_EPI_WARPS * QT * kDepth);  // [4][QT]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(thr + RR_TC_EPI_WARPS * QT);
+    // bars: full[kMaxStages], empty[kMaxStages], acc_full[kAccStages], acc_empty[kAccStages], qfull
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + kMaxStages;
+    uint64_t* bar_acc_full = bars + 2 * kMaxStages;
+    uint64_t* bar_acc_empty = bar_acc_full + kAccStages;
+    uint64_t* bar_q = bar_acc_empty + kAccStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_q + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    constexpr uint32_t kTmemCols = (kAccStages * QT < 32) ? 32 : kAccStages * QT;  // 64/128/256
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        tma_prefetch_desc(&tmap_q);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(smem_u32(bar_full + i), 1);
+            mbar_init(smem_u32(bar_empty + i), 1);
+        }
+        for (int i = 0; i < kAccStages; ++i) {
+            mbar_init(smem_u32(bar_acc_full + i), 1);
+            mbar_init(smem_u32(bar_acc_empty + i), RR_TC_EPI_WARPS);
+        }
+        mbar_init(smem_u32(bar_q), 1);
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            mbar_arrive_expect_tx(smem_u32(bar_q), (uint32_t)q_bytes);
+            for (int kc = 0; kc < p.num_kc; ++kc)
+                tma_load_2d(smem_u32(q_sm + kc * QT * 128), &tmap_q, smem_u32(bar_q), kc * RR_TC_KCHUNK,
+                            p.q_row0, kEvictLast);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                for (int kc = 0; kc < p.num_kc; ++kc) {
+                    mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
+                    tma_load_2d(smem_u32(x_sm + stage * kStageBytes), &tmap_x, smem_u32(bar_full + stage),
+                                kc * RR_TC_KCHUNK, tile * RR_TC_TILE_ROWS, kEvictFirst);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(RR_TC_TILE_ROWS, QT);
+            mbar_wait(smem_u32(bar_q), 0);
+            tc_fence_after();
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * QT);
+                for (int kc = 0; kc < p.num_kc; ++kc) {
+                    mbar_wait(smem_u32(bar_full + stage), phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(x_sm + stage * kStageBytes);
+                    const uint32_t b_addr = smem_u32(q_sm + kc * QT * 128);
+#pragma unroll
+                    for (int k = 0; k < RR_TC_KCHUNK / 16; ++k) {
+                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
+                                  idesc, (uint32_t)((kc | k) != 0));
+                    }
+                    umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete -> epilogue
+                if (++acc == kAccStages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps 2..5 ===========================
+        const int ew = warp - 2;
+        const int quad = warp & 3;  // TMEM lanes [32*quad, 32*quad+32) are this warp's
+        float* ls_w = ls + ew * QT * kDepth;
+        uint32_t* lr_w = lr + ew * QT * kDepth;
+        float* thr_w = thr + ew * QT;
+        for (int i = lane; i < QT * kDepth; i += 32) {
+            ls_w[i] = RR_NEG_INF;
+            lr_w[i] = RR_NO_ROW;
+        }
+        for (int q = lane; q < QT; q += 32)
+            thr_w[q] = (q < p.nq_tile && p.active[q]) ? RR_NEG_INF : __builtin_huge_valf();
+        __syncwarp();
+
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(smem_u32(bar_acc_full + acc), acc_phase);
+            tc_fence_after();
+            const int64_t row64 = (int64_t)tile * RR_TC_TILE_ROWS + quad * 32 + lane;
+            const bool valid = row64 < p.n_rows;
+            const uint32_t row = (uint32_t)row64;
+            const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * QT);
+#pragma unroll 1
+            for (int c0 = 0; c0 < QT; c0 += 16) {
+                float v[16];
+                tmem_ld_x16(t_row + (uint32_t)c0, v);
+                unsigned mine = 0;
+#pragma unroll
+                for (int j4 = 0; j4 < 4; ++j4) {
+                    const float4 t4 = *reinterpret_cast<const float4*>(thr_w + c0 + j4 * 4);
+                    mine |= (v[j4 * 4 + 0] > t4.x ? 1u : 0u) << (j4 * 4 + 0);
+                    mine |= (v[j4 * 4 + 1] > t4.y ? 1u : 0u) << (j4 * 4 + 1);
+                    mine |= (v[j4 * 4 + 2] > t4.z ? 1u : 0u) << (j4 * 4 + 2);
+                    mine |= (v[j4 * 4 + 3] > t4.w ? 1u : 0u) << (j4 * 4 + 3);
+                }
+                if (!valid) mine = 0;
+                if (__any_sync(RR_FULL, mine != 0)) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const unsigned b = __ballot_sync(RR_FULL, (mine >> j) & 1u);
+                        if (b)
+                            epi_take(v[j], b, row, ls_w + (c0 + j) * kDepth, lr_w + (c0 + j) * kDepth,
+                                     thr_w + c0 + j, lane);
+                    }
+                }
+            }
+            // all TMEM reads of this stage are complete (wait::ld): hand it back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bar_acc_empty + acc));
+            if (++acc == kAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+        }
+        // publish this warp's lists: [query][list = cta*4 + ew][kDepth]
+        const int64_t list = (int64_t)blockIdx.x * RR_TC_EPI_WARPS + ew;
+        for (int i = lane; i < p.nq_tile * kDepth; i += 32) {
+            const int q = i / kDepth, e = i - q * kDepth;
+            const int64_t o = (int64_t)q * p.cand_stride + list * kDepth + e;
+            p.cand_s[o] = ls_w[i];
+            p.cand_r[o] = lr_w[i];
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------ host ----
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int d_pad, int box_rows) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) {
+        rr_set_error("cuTensorMapEncodeTiled is not available from the driver");
+        return RR_ERR_CUDA;
+    }
+    cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
+    cuuint32_t box[2] = {(cuuint32_t)RR_TC_KCHUNK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        rr_set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld d_pad=%d box_rows=%d", (int)r,
+                     (long long)rows, d_pad, box_rows);
+        return RR_ERR_CUDA;
+    }
+    return RR_OK;
+}
+
+struct SmemPlan {
+    int stages;
+    size_t bytes;
+};
+
+SmemPlan plan_smem(int d_pad, int qt) {
+    const size_t q_bytes = (size_t)d_pad * 2 * qt;
+    const size_t lists = (size_t)RR_TC_EPI_WARPS * qt * kDepth * 8 + (size_t)RR_TC_EPI_WARPS * qt * 4;
+    const size_t bars = (2 * kMaxStages + 2 * kAccStages + 1) * 8 + 16;
+    const size_t fixed = 1024 /*alignment slack*/ + q_bytes + lists + bars;
+    SmemPlan pl{0, 0};
+    if (fixed + 2 * (size_t)kStageBytes > (size_t)kSmemLimit) return pl;
+    pl.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / kStageBytes);
+    pl.bytes = fixed + (size_t)pl.stages * kStageBytes;
+    return pl;
+}
+
+template <int QT>
+int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem,
+              cudaStream_t stream) {
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_tc_scan_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemLimit));
+        attr_done[h->device & 63] = true;
+    }
+    rr_tc_scan_kernel<QT><<<grid, kThreads, smem, stream>>>(h->tmap_hi, tq, p);
+    RR_CUDA_CHECK(cudaGetLastError());
+    return RR_OK;
+}
+
+}  // namespace
+
+int rr_tc_scan_qtile(const rr_index* h) {
+    if (h->d_pad <= 1024) return 64;
+    if (h->d_pad <= 2048) return 32;
+    if (h->d_pad <= 4096) return 16;
+    return 0;
+}
+
+int rr_tc_scan_num_lists(const rr_index* h) { return h->sm_count * RR_TC_EPI_WARPS; }
+
+int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
+                      const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
+                      int64_t cand_stride, int* n_lists_out, cudaStream_t stream) {
+    const int qt = rr_tc_scan_qtile(h);
+    RR_REQUIRE(qt > 0 && nq_tile >= 1 && nq_tile <= qt, "rr_tc_scan_launch: bad query tile");
+    const SmemPlan pl = plan_smem(h->d_pad, qt);
+    RR_REQUIRE(pl.stages >= 2, "rr_tc_scan_launch: shared memory plan failed for d_pad=%d", h->d_pad);
+    if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
+        int rc = make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, RR_TC_TILE_ROWS);
+        if (rc != RR_OK) return rc;
+        h->tmap_hi_ptr = h->hi;
+        h->tmap_hi_rows = h->n;
+    }
+    alignas(64) CUtensorMap tq;
+    int rc = make_tmap_bf16_rows(&tq, qbf16_dev, q_rows_total, h->d_pad, qt);
+    if (rc != RR_OK) return rc;
+
+    TcParams p;
+    p.n_rows = h->n;
+    p.n_tiles = (int)((h->n + RR_TC_TILE_ROWS - 1) / RR_TC_TILE_ROWS);
+    p.num_kc = h->d_pad / RR_TC_KCHUNK;
+    p.nq_tile = nq_tile;
+    p.q_row0 = q_row0;
+    p.stages = pl.stages;
+    p.active = active_dev;
+    p.any_active = any_active_dev;
+    p.cand_s = cand_s;
+    p.cand_r = cand_r;
+    p.cand_stride = cand_stride;
+    const int grid = std::min(h->sm_count, p.n_tiles);
+    *n_lists_out = grid * RR_TC_EPI_WARPS;
+    switch (qt) {
+        case 64: return launch_qt<64>(h, tq, p, grid, pl.bytes, stream);
+        case 32: return launch_qt<32>(h, tq, p, grid, pl.bytes, stream);
+        default: return launch_qt<16>(h, tq, p, grid, pl.bytes, stream);
+    }
+}

@@ -1,0 +1,15 @@
+#!/bin/bash
+# Run the GPU suite as separate processes so one CUDA fault does not hide the rest.
+# Usage (on the GPU box, from the repo root): bash scripts/gpu_tests_split.sh
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+run() { # name, pytest args...
+  local name=$1; shift
+  timeout 900 python -m pytest "$@" -q --timeout 600 -p no:cacheprovider > gpurun_out/$name.log 2>&1
+  echo "$name exit=$? $(tail -1 gpurun_out/$name.log)"
+}
+run router_rerank tests/test_gpu_router_rerank.py
+run index_exact tests/test_gpu_index.py -k "exact or reconstruct or normalize or errors or offset"
+run index_tcscan tests/test_gpu_index.py -k "tc_scan_candidates"
+run index_auto tests/test_gpu_index.py -k "not exact and not tc_scan_candidates and not reconstruct and not normalize and not errors and not offset"
+run federation tests/test_gpu_federation.py

@@ -1,0 +1,235 @@
+"""Parity of the CUDA flat-IP index (through the C ABI) with the CPU oracle.
+
+Tolerances (north_star): ids equal to the oracle's FAISS-fp32 restatement except
+ids whose float64 score is within 1e-5 relative of the k-th score (documented
+ties); scores within 1e-5 relative.  'auto' (tcgen05 bf16 scan + exact rescoring +
+certificate) must return bit-identical results to 'exact'."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import flat_ip as oracle
+from ragroute_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+FLT_MAX = np.finfo(np.float32).max
+
+
+@pytest.fixture(scope="module")
+def faiss(cuda_required):
+    import ragroute_b200.faiss_compat as faiss
+    return faiss
+
+
+def _index(faiss, xb, mode="auto"):
+    ix = faiss.IndexFlatIP(xb.shape[1])
+    ix.add(xb)
+    ix.set_mode(mode)
+    return ix
+
+
+def _check_vs_oracle(faiss, xb, q, k, mode, expect_no_rescan=False):
+    ix = _index(faiss, xb, mode)
+    D, I = ix.search(q, k)
+    Dr, Ir = oracle.search(q, xb, k)
+    info = oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    st = ix.stats()
+    if expect_no_rescan:
+        assert st["exact_rescans"] == 0, f"certificate failed on benign data: {st}"
+    return D, I, info, st
+
+
+@pytest.mark.parametrize("mode", ["exact", "auto"])
+def test_hand_computable_duplicates(faiss, mode):
+    xb = np.zeros((64, 8), dtype=np.float32)
+    for j in range(64):
+        xb[j, j % 8] = j // 8 + 1
+    xb[10] = xb[58]
+    q = np.zeros((1, 8), dtype=np.float32)
+    q[0, 2] = 2.0
+    D, I = _index(faiss, xb, mode).search(q, 5)
+    assert D[0].tolist() == [16.0, 16.0, 14.0, 12.0, 10.0]
+    assert I[0].tolist() == [10, 58, 50, 42, 34]   # ties: lower row id first (deterministic)
+
+
+@pytest.mark.parametrize("mode", ["exact", "auto"])
+def test_fewer_rows_than_k_and_empty(faiss, mode):
+    rng = np.random.default_rng(1)
+    xb = rng.standard_normal((5, 16), dtype=np.float32)
+    q = rng.standard_normal((3, 16), dtype=np.float32)
+    D, I = _index(faiss, xb, mode).search(q, 8)
+    Dr, Ir = oracle.search_seq(q, xb, 8)
+    oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    assert (I[:, 5:] == -1).all() and (D[:, 5:] == -FLT_MAX).all()
+    ix = faiss.IndexFlatIP(16)
+    ix.set_mode(mode)
+    D0, I0 = ix.search(q, 4)
+    assert (I0 == -1).all() and (D0 == -FLT_MAX).all()
+
+
+@pytest.mark.parametrize("mode", ["exact", "auto"])
+@pytest.mark.parametrize("n,d,k,nq", [(5000, 768, 32, 5), (3000, 1024, 10, 3), (4000, 384, 10, 7),
+                                      (2500, 100, 7, 2), (700, 4096, 10, 2), (129, 768, 32, 1)])
+def test_random_gaussian_vs_oracle(faiss, mode, n, d, k, nq):
+    rng = np.random.default_rng(n + d)
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    _check_vs_oracle(faiss, xb, q, k, mode)
+
+
+def test_medrag_shaped_corpus_auto_equals_exact_without_rescans(faiss):
+    d, k = 768, 32
+    xb = syn.corpus_rows(2, 60000, d)
+    q = syn.queries(64, d, [2], seed=3)
+    Da, Ia, info, st = _check_vs_oracle(faiss, xb, q, k, "auto", expect_no_rescan=True)
+    De, Ie = _index(faiss, xb, "exact").search(q, k)
+    assert np.array_equal(Ia, Ie) and np.array_equal(Da, De), "auto and exact must agree bit for bit"
+    assert st["queries"] == 64
+
+
+def test_batches_larger_than_one_pass_and_chunk(faiss):
+    d, k = 768, 10
+    xb = syn.corpus_rows(1, 20000, d)
+    q = syn.queries(300, d, [1], seed=9)       # > 64 (one tc pass) and > 256 (one chunk)
+    D, I, _, st = _check_vs_oracle(faiss, xb, q, k, "auto", expect_no_rescan=True)
+    D1, I1 = _index(faiss, xb, "auto").search(q[17:18], k)  # same answer alone as in the batch
+    assert np.array_equal(I1[0], I[17]) and np.array_equal(D1[0], D[17])
+
+
+def test_tc_scan_candidates_match_bf16_reference(faiss):
+    """The raw tensor-core scan: the union of its candidate lists must contain the
+    top rows of a bf16-input / fp32-accumulate reference, with matching scores."""
+    d = 768
+    xb = syn.corpus_rows(0, 30000, d)
+    q = syn.queries(9, d, [0], seed=4)
+    ix = _index(faiss, xb, "auto")
+    qt = torch.from_numpy(q).cuda()
+    cs, cr, n_lists, depth = ix.debug_tc_candidates(qt)
+    torch.cuda.synchronize()
+    cs, cr = cs.cpu().numpy(), cr.cpu().numpy().astype(np.int64) & 0xFFFFFFFF
+
+    def bf16_rna(a):  # the library's rounding: nearest, ties away (bits + 0x8000) >> 16
+        b = (a.view(np.uint32) + np.uint32(0x8000)) & np.uint32(0xFFFF0000)
+        return b.view(np.float32)
+
+    ref = bf16_rna(q).astype(np.float64) @ bf16_rna(xb).astype(np.float64).T
+    for b in range(q.shape[0]):
+        valid = cr[b] != 0xFFFFFFFF
+        rows, sc = cr[b][valid], cs[b][valid]
+        assert len(np.unique(rows)) == len(rows), "a row appears in two candidate lists"
+        np.testing.assert_allclose(sc, ref[b][rows], rtol=0, atol=2e-5)
+        top = np.argsort(-ref[b])[:64]
+        assert set(top.tolist()) <= set(rows.tolist()), "tensor-core scan lost a top-64 row"
+    assert depth == 16 and n_lists >= 4
+
+
+def test_adversarial_near_ties_fall_back_to_exact(faiss):
+    """Rows identical after bf16 rounding but different in fp32: the bf16 scan cannot
+    rank them, the certificate must notice and the exact path must return the fp32
+    order."""
+    d, k, n = 768, 32, 4096
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal(d).astype(np.float32)
+    base = ((base.view(np.uint32) + np.uint32(0x8000)) & np.uint32(0xFFFF0000)).view(np.float32)  # exactly bf16
+    xb = np.tile(base, (n, 1))
+    # perturb below bf16 resolution (relative 2^-10 < half an ulp = 2^-8), different per row
+    xb *= (1.0 + rng.uniform(-1, 1, size=(n, 1)).astype(np.float32) * np.float32(2.0 ** -10))
+    q = base[None, :].copy()
+    ix = _index(faiss, xb, "auto")
+    D, I = ix.search(q, k)
+    Dr, Ir = oracle.search_seq(q, xb, k)
+    oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    assert ix.stats()["exact_rescans"] >= 1, "the certificate should have rejected the bf16 ranking"
+    # the library's own contract: fp64-accumulated score rounded to fp32, ties by lower id
+    t32 = (xb.astype(np.float64) @ q[0].astype(np.float64)).astype(np.float32)
+    want = np.lexsort((np.arange(n), -t32.astype(np.float64)))[:k]
+    assert I[0].tolist() == want.tolist() and np.array_equal(D[0], t32[want])
+
+
+def test_all_rows_identical(faiss):
+    xb = np.ones((1000, 64), dtype=np.float32)
+    q = np.ones((2, 64), dtype=np.float32)
+    for mode in ("exact", "auto"):
+        D, I = _index(faiss, xb, mode).search(q, 8)
+        assert (D == 64.0).all() and I[0].tolist() == list(range(8))
+
+
+def test_search_tensor_mask_and_strided_output(faiss):
+    d, k = 768, 32
+    xb = syn.corpus_rows(2, 9000, d)
+    q = syn.queries(12, d, [2], seed=8)
+    ix = _index(faiss, xb, "auto")
+    qt = torch.from_numpy(q).cuda()
+    mask = torch.zeros((12, 3), dtype=torch.uint8, device="cuda")
+    mask[::2, 1] = 1
+    D_all = torch.full((12, 3 * k), 7.0, dtype=torch.float32, device="cuda")
+    I_all = torch.full((12, 3 * k), 7, dtype=torch.int64, device="cuda")
+    ix.search_tensor(qt, k, mask=mask, mask_col=1, out=(D_all, I_all), out_col=k)
+    torch.cuda.synchronize()
+    D_all, I_all = D_all.cpu().numpy(), I_all.cpu().numpy()
+    Dr, Ir = ix.search(q, k)
+    assert (D_all[:, :k] == 7).all() and (I_all[:, 2 * k:] == 7).all(), "wrote outside its columns"
+    assert np.array_equal(I_all[::2, k:2 * k], Ir[::2]) and np.array_equal(D_all[::2, k:2 * k], Dr[::2])
+    assert (I_all[1::2, k:2 * k] == -1).all() and (D_all[1::2, k:2 * k] == -FLT_MAX).all()
+    # nothing routed at all: padding everywhere, corpus untouched
+    mask.zero_()
+    D2, I2 = ix.search_tensor(qt, k, mask=mask, mask_col=0)
+    assert (I2 == -1).all().item()
+
+
+def test_id_offset_and_incremental_add(faiss):
+    d, k = 384, 10
+    xb = syn.corpus_rows(1, 3000, d)
+    q = syn.queries(4, d, [1], seed=2)
+    ix = faiss.IndexFlatIP(d)
+    ix.add(xb[:1000])
+    ix.add(torch.from_numpy(xb[1000:]).cuda())     # device-side add, grows the planes
+    assert ix.ntotal == 3000
+    D, I = ix.search(q, k)
+    Dr, Ir = oracle.search_seq(q, xb, k)
+    oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    ix.set_id_offset(1_000_000_000_000)
+    D2, I2 = ix.search(q, k)
+    assert np.array_equal(I2, I + 1_000_000_000_000) and np.array_equal(D2, D)
+
+
+def test_reconstruct_is_bit_exact_and_index_file_roundtrip(faiss):
+    rng = np.random.default_rng(3)
+    xb = rng.standard_normal((777, 100), dtype=np.float32)
+    xb[0, :4] = [0.0, -0.0, 1e-30, 3.0e38]
+    ix = _index(faiss, xb)
+    back = ix.reconstruct_n(0, 777)
+    assert np.array_equal(back.view(np.uint32), xb.view(np.uint32)), "hi/lo planes must rebuild fp32 exactly"
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "faiss.index")
+        faiss.write_index(ix, path)
+        ix2 = faiss.read_index(path)
+        assert ix2.ntotal == 777 and ix2.d == 100
+        q = rng.standard_normal((2, 100), dtype=np.float32)
+        a, b = ix.search(q, 5), ix2.search(q, 5)
+        assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
+
+
+def test_normalize_l2_matches_oracle(faiss):
+    rng = np.random.default_rng(2)
+    x = rng.standard_normal((3, 768), dtype=np.float32)
+    x[1] = 0
+    y, z = x.copy(), x.copy()
+    faiss.normalize_L2(y)
+    oracle.normalize_L2(z)
+    np.testing.assert_allclose(y, z, rtol=1e-6, atol=1e-8)
+    assert (y[1] == 0).all()
+
+
+def test_errors_like_faiss(faiss):
+    ix = _index(faiss, np.ones((10, 8), dtype=np.float32))
+    with pytest.raises(AssertionError):
+        ix.search(np.ones((1, 9), dtype=np.float32), 3)     # wrong d
+    with pytest.raises(AssertionError):
+        ix.search(np.ones((1, 8), dtype=np.float32), 0)     # k must be > 0
+    from ragroute_b200._lib import RRError
+    with pytest.raises(RRError):
+        ix.search(np.ones((1, 8), dtype=np.float32), 33)    # k > RR_MAX_K: loud, not silent

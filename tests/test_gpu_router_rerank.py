@@ -1,0 +1,108 @@
+"""Parity of the fused router kernel and the merge kernel (through the C ABI) with
+the golden vectors recorded from the reference's own code and with the numpy
+oracles.  Tolerances: logits within 1e-5 absolute; source selections identical
+except logits within 1e-5 of the decision threshold; merge bit-exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from golden_util import GOLDEN, RouterCase
+from oracle import rerank_ref, router_ref
+
+pytestmark = pytest.mark.gpu
+
+
+def _make_router(c):
+    from ragroute_b200.router import FusedCorpusRouter
+    r = FusedCorpusRouter(c.in_dim)
+    r.load_state_dict({k: torch.from_numpy(v) for k, v in c.sd.items()})
+    r.eval()
+    r.set_tables(c.data_sources, c.d_max, c.model_of_source, c.centroids, c.onehot_ids, c.n_onehot, c.scaler)
+    return r
+
+
+@pytest.mark.parametrize("dataset", ["medrag", "feb4rag", "wikipedia"])
+def test_router_matches_reference_golden(cuda_required, dataset):
+    c = RouterCase(dataset)
+    r = _make_router(c)
+    assert r.fc1.in_features == c.in_dim
+    thr_logit = router_ref.logit_threshold(c.threshold)
+    # batched select over all golden queries at once
+    slots = r.slot_names
+    q = np.zeros((c.n_queries, len(slots), c.d_max), dtype=np.float32)
+    for qi in range(c.n_queries):
+        emb = c.query(qi)
+        for si, m in enumerate(slots):
+            q[qi, si, :len(emb[m])] = emb[m]
+    mask, logits = r.select(torch.from_numpy(q).cuda(), c.threshold, return_logits=True)
+    torch.cuda.synchronize()
+    mask, logits = mask.cpu().numpy().astype(bool), logits.cpu().numpy()
+    np.testing.assert_allclose(logits, c.ref_logits, rtol=0, atol=1e-5)
+    decided = np.abs(c.ref_logits - thr_logit) > 1e-5
+    assert np.array_equal(mask[decided], c.ref_masks[decided])
+    # one query through the reference's own signature
+    names = r.select_relevant_sources(c.query(0), c.threshold)
+    ref_names = [s for s, m in zip(c.data_sources, c.ref_masks[0]) if m]
+    undecided = {s for s, dcd in zip(c.data_sources, decided[0]) if not dcd}
+    assert set(names) ^ set(ref_names) <= undecided
+    assert names == [s for s in c.data_sources if s in names]      # data_sources order
+    # module call on explicit feature rows == oracle features -> same logits
+    feats = router_ref.build_features(c.query(3), c.data_sources, c.model_of_source, c.centroids,
+                                      c.onehot_ids, c.n_onehot, c.d_max)
+    if c.scaler:
+        feats = (feats - c.scaler[0]) / c.scaler[1]
+    out = r(torch.tensor(feats, dtype=torch.float32)).cpu().numpy()
+    assert out.shape == (len(c.data_sources), 1)
+    np.testing.assert_allclose(out[:, 0], c.ref_logits[3], rtol=0, atol=1e-5)
+
+
+def test_router_batch_sizes_and_errors(cuda_required):
+    c = RouterCase("medrag")
+    r = _make_router(c)
+    rng = np.random.default_rng(0)
+    for B in (1, 3, 4, 5, 64, 257):
+        q = rng.uniform(-0.4, 0.4, size=(B, c.d_max)).astype(np.float32)
+        mask, logits = r.select(torch.from_numpy(q).cuda(), c.threshold, return_logits=True)
+        logits = logits.cpu().numpy()
+        for b in (0, B - 1):
+            feats = router_ref.build_features({c.models[0]: q[b]}, c.data_sources, c.model_of_source,
+                                              c.centroids, c.onehot_ids, c.n_onehot, c.d_max)
+            m_ref, l_ref = router_ref.select(c.sd, feats, c.threshold, *c.scaler)
+            np.testing.assert_allclose(logits[b], l_ref, rtol=0, atol=1e-5)
+    from ragroute_b200.router import FusedCorpusRouter
+    from ragroute_b200._lib import RRError
+    with pytest.raises(RRError):
+        FusedCorpusRouter(10)(torch.zeros(1, 10))      # used before load_state_dict
+    with pytest.raises(KeyError):
+        FusedCorpusRouter(10).load_state_dict({})
+
+
+def test_rerank_matches_reference_golden(cuda_required):
+    from ragroute_b200 import rerank
+    g = np.load(os.path.join(GOLDEN, "rerank.npz"))
+    for ci in range(int(g["n_cases"])):
+        scores = g[f"c{ci}_scores"]
+        k = int(g[f"c{ci}_k"])
+        docs = [f"doc{i}" for i in range(len(scores))]
+        s_list = [float(v) for v in scores]
+        d1, s1 = rerank.rerank_medrag(docs, s_list, k)
+        d2, s2 = rerank.rerank_wikipedia(docs, s_list, k)
+        assert d1 == [f"doc{i}" for i in g[f"c{ci}_medrag_docs"]] and s1 == g[f"c{ci}_medrag_scores"].tolist()
+        assert d2 == [f"doc{i}" for i in g[f"c{ci}_wikipedia_docs"]] and s2 == g[f"c{ci}_wikipedia_scores"].tolist()
+
+
+@pytest.mark.parametrize("B,L,k", [(1, 128, 32), (7, 96, 32), (33, 1024, 32), (5, 40, 10), (3, 4096, 32), (2, 5, 8)])
+@pytest.mark.parametrize("descending", [True, False])
+def test_merge_topk_vs_oracle_with_ties_and_holes(cuda_required, B, L, k, descending):
+    from ragroute_b200.rerank import merge_topk
+    rng = np.random.default_rng(B * 1000 + L)
+    scores = rng.integers(0, 50, size=(B, L)).astype(np.float32) / 4     # many exact ties
+    ids = rng.integers(0, 1 << 40, size=(B, L)).astype(np.int64)
+    ids[rng.random((B, L)) < 0.2] = -1                                   # empty slots (faiss padding)
+    scores[ids < 0] = -np.finfo(np.float32).max
+    s, i, p = merge_topk(torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda(), k, descending)
+    rs, ri, rp = rerank_ref.merge_topk(scores, ids, k, descending)
+    assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(p.cpu().numpy(), rp)
