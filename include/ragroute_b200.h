@@ -53,6 +53,8 @@ int rr_abi_version(void);
 const char* rr_last_error(void);
 /* number of visible CUDA devices, or a negative rr_status */
 int rr_device_count(void);
+/* kernels this library has launched in this process (benchmark bookkeeping) */
+int64_t rr_kernel_launches(void);
 
 /* ---------------------------------------------------- B1: flat IP index -- */
 /* Search modes (rr_index_set_param "mode") */

@@ -38,6 +38,7 @@ _SIGNATURES = {
     "rr_abi_version": (c_int, []),
     "rr_last_error": (c_char_p, []),
     "rr_device_count": (c_int, []),
+    "rr_kernel_launches": (c_int64, []),
     "rr_index_create": (c_int, [c_int, c_int64, c_int, POINTER(c_void_p)]),
     "rr_index_destroy": (c_int, [c_void_p]),
     "rr_index_reserve": (c_int, [c_void_p, c_int64]),

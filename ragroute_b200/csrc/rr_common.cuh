@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/ragroute_b200.h"
@@ -43,6 +44,7 @@ struct rr_device_guard {
 };
 
 int rr_check_device_arch(int device);  // RR_OK iff compute capability 10.x
+void rr_count_launch(int n);            // process-wide count of this library's kernel launches
 
 constexpr float RR_NEG_INF = -__builtin_huge_valf();
 constexpr uint32_t RR_NO_ROW = 0xFFFFFFFFu;

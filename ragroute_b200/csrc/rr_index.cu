@@ -145,7 +145,7 @@ rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
     }
 }
 
-// Exact scan over the queries in fail_list[sub*qsub ...): fp32 rows rebuilt from
+// Exact scan over the queries in fail_list[blockIdx.y*qsub ...): fp32 rows rebuilt from
 // the planes, products and sums in fp64 (each product of two fp32 is exact in
 // fp64), score rounded once to fp32.  One warp per row; per-warp lists of depth
 // 32 per query, merged per block at the end.
@@ -155,10 +155,10 @@ __global__ void __launch_bounds__(RR_EXACT_WARPS * 32)
 rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
                      int64_t n_rows, int d_pad, const float* __restrict__ q, int d,
                      const int* __restrict__ fail_list, const rr_chunk_ctl* __restrict__ ctl,
-                     int sub, int qsub, float* __restrict__ cand_s,
+                     int qsub, float* __restrict__ cand_s,
                      uint32_t* __restrict__ cand_r, int64_t cand_stride) {
     const int n_fail = ctl->n_fail;
-    const int q0 = sub * qsub;
+    const int q0 = (int)blockIdx.y * qsub;  // blockIdx.y = sub-batch of failing queries
     if (q0 >= n_fail) return;
     const int nq = min(qsub, n_fail - q0);
     constexpr int M = RR_EXACT_LIST_DEPTH;
@@ -815,6 +815,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
                                                        qbf, qnorm, active, fail_flags, fail_list, ctl,
                                                        use_tc ? 0 : 1);
     RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(1);
 
     rr_finalize_args fa;
     fa.cand_s = cand_s;
@@ -858,6 +859,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
                                        cand_s + (size_t)p0 * cand_stride, cand_r + (size_t)p0 * cand_stride,
                                        cand_stride, &n_lists, stream);
             if (rc != RR_OK) return rc;
+            rr_count_launch(1);
             if (prof) {
                 RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
                 h->ev_bytes[h->ev_used / 2] = h->n * (int64_t)h->d_pad * 2;
@@ -868,6 +870,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
         }
         rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
         RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
     }
 
     // exact path over fail_list (everything when !use_tc); launches exit at once when empty
@@ -884,17 +887,18 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     }
     RR_REQUIRE(ex_smem <= (200u << 10), "dimension %d too large for the exact scan kernel", h->d);
     if (h->n > 0) {
-        for (int sub = 0; sub * qsub < nq; ++sub) {
-            rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<g_exact, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
-                h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, fail_list, ctl, sub, qsub, cand_s, cand_r,
-                cand_stride);
-            RR_CUDA_CHECK(cudaGetLastError());
-        }
+        // one launch covers every sub-batch; blocks beyond the failing queries exit at once
+        const dim3 grid((unsigned)g_exact, (unsigned)((nq + qsub - 1) / qsub));
+        rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
+            h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, fail_list, ctl, qsub, cand_s, cand_r, cand_stride);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
     }
     fa.n_lists = (h->n > 0) ? g_exact : 0;
     fa.depth = RR_EXACT_LIST_DEPTH;
     rr_finalize_kernel<false><<<nq, RR_FIN_THREADS, 0, stream>>>(fa);
     RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(1);
     return RR_OK;
 }
 

@@ -99,5 +99,6 @@ extern "C" int rr_merge_topk(const float* s_dev, const int64_t* id_dev, int64_t 
     rr_merge_topk_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
         s_dev, id_dev, B, L, k, descending, os_dev, oid_dev, opos_dev);
     RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(1);
     return RR_OK;
 }

@@ -224,6 +224,7 @@ int router_launch(rr_router* h, const RouterArgs& a, cudaStream_t stream) {
     const unsigned blocks = (unsigned)((a.B + kQB - 1) / kQB);
     rr_router_kernel<<<blocks, kThreads, smem, stream>>>(a);
     RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(1);
     (void)h;
     return RR_OK;
 }
