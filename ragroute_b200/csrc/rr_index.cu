@@ -602,7 +602,7 @@ extern "C" int rr_index_destroy(rr_index_t* h) {
     if (!h) return RR_OK;
     rr_device_guard g(h->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 64; ++i)
+    for (int i = 0; i < rr_index::kEvPool; ++i)
         if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
     cudaFree(h->hi);
     cudaFree(h->lo);
@@ -743,7 +743,6 @@ static int rr_flush_events(rr_index* h) {
         RR_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
         h->stats.scan_ms_total += ms;
         h->stats.scan_launches += 1;
-        h->stats.scan_bytes_total += h->ev_bytes[i / 2];
     }
     h->ev_used = 0;
     return RR_OK;
@@ -754,14 +753,16 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
     rr_device_guard g(h->device);
     int rc = rr_flush_events(h);
     if (rc != RR_OK) return rc;
-    int nf = 0;
-    RR_CUDA_CHECK(cudaMemcpy(&nf, h->d_nfail_total, sizeof(int), cudaMemcpyDeviceToHost));
-    h->stats.exact_rescans = nf;
+    unsigned long long ctr[2] = {0, 0};  // [0] low int = certificate failures, [1] = bytes really scanned
+    RR_CUDA_CHECK(cudaMemcpy(ctr, h->d_nfail_total, 16, cudaMemcpyDeviceToHost));
+    h->stats.exact_rescans = (int)(ctr[0] & 0xFFFFFFFFull);
+    h->stats.scan_bytes_total = (int64_t)ctr[1];
     *out = h->stats;
     if (reset) {
         h->stats.scan_ms_total = 0;
         h->stats.scan_launches = 0;
         h->stats.scan_bytes_total = 0;
+        RR_CUDA_CHECK(cudaMemset(h->d_nfail_total + 2, 0, 8));
     }
     return RR_OK;
 }
@@ -845,19 +846,18 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
         for (int p0 = 0; p0 < nq; p0 += qt) {
             const int nqt = std::min(qt, nq - p0);
             int n_lists = 0;
-            const bool prof = h->profile != 0;
+            // never synchronise inside a search: a full pool just stops recording
+            const bool prof = h->profile != 0 && h->ev_used + 2 <= rr_index::kEvPool;
             if (prof) {
-                if (h->ev_used + 2 > 64) {
-                    int rc = rr_flush_events(h);
-                    if (rc != RR_OK) return rc;
-                }
                 for (int i = 0; i < 2; ++i)
                     if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
                 RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
             }
             int rc = rr_tc_scan_launch(h, qbf, nq_pad, p0, nqt, active + p0, &ctl->any_active,
                                        cand_s + (size_t)p0 * cand_stride, cand_r + (size_t)p0 * cand_stride,
-                                       cand_stride, &n_lists, stream);
+                                       cand_stride, &n_lists,
+                                       prof ? reinterpret_cast<unsigned long long*>(h->d_nfail_total + 2) : nullptr,
+                                       stream);
             if (rc != RR_OK) return rc;
             rr_count_launch(1);
             if (prof) {
@@ -1012,7 +1012,7 @@ extern "C" int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq,
     RR_CUDA_CHECK(cudaMemsetAsync(cand_s_dev, 0xFF, (size_t)nq * capacity * sizeof(float), stream));
     RR_CUDA_CHECK(cudaMemsetAsync(cand_r_dev, 0xFF, (size_t)nq * capacity * sizeof(uint32_t), stream));
     int rc = rr_tc_scan_launch(h, (uint16_t*)(base + o_qbf), nq_pad, 0, nq, (uint8_t*)(base + o_act),
-                               &ctl->any_active, cand_s_dev, cand_r_dev, capacity, n_lists, stream);
+                               &ctl->any_active, cand_s_dev, cand_r_dev, capacity, n_lists, nullptr, stream);
     if (rc != RR_OK) return rc;
     *depth = RR_TC_LIST_DEPTH;
     return RR_OK;

@@ -48,10 +48,11 @@ struct rr_index {
 
     // stats
     rr_index_stats stats = {};
-    int* d_nfail_total = nullptr;  // device counter of certificate failures
-    cudaEvent_t ev_pool[64] = {};
+    int* d_nfail_total = nullptr;  // device: [0] certificate failures (int); bytes 8..15: scanned-bytes counter (u64)
+    static constexpr int kEvPool = 4096;  // 2048 timed launches between two rr_index_get_stats calls
+    cudaEvent_t ev_pool[kEvPool] = {};
     int ev_used = 0;
-    int64_t ev_bytes[32] = {};
+    int64_t ev_bytes[kEvPool / 2] = {};
 };
 
 // rr_scan_tc.cu: launch the tcgen05 scan for one pass of <= qtile queries: rows
@@ -61,7 +62,8 @@ struct rr_index {
 // the pass's first query) and reports the number of lists per query.
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
-                      int64_t cand_stride, int* n_lists_out, cudaStream_t stream);
+                      int64_t cand_stride, int* n_lists_out, unsigned long long* bytes_scanned_dev,
+                      cudaStream_t stream);
 // number of candidate lists per query the tc scan produces for this index
 int rr_tc_scan_num_lists(const rr_index* h);
 // queries per pass for this dimension (stationary query tile must fit in smem)

@@ -31,10 +31,10 @@ def smoke() -> None:
     names, sids, corpora, sd, scaler, centroids = build_small_medrag(d=d)
     q = syn.queries(B, d, sids, seed=5)
 
-    router = FusedCorpusRouter(2 * d + 4)
-    router.load_state_dict(sd)
-    router.set_tables(names, d, {n: "ncbi/MedCPT-Query-Encoder" for n in names}, centroids,
-                      {n: syn.MEDRAG_SOURCE_TO_ID[n] for n in names}, 4, scaler)
+    # seeded router whose fc3 bias is calibrated so that about half the pairs are routed
+    from .workloads import make_synthetic_router
+    router = make_synthetic_router(names, d, centroids, 11, 0)
+    sd, scaler = router.synthetic_state["sd"], router.synthetic_state["scaler"]
     sources = {}
     for n in names:
         ix = IndexFlatIP(d)
@@ -72,6 +72,7 @@ def smoke() -> None:
             for (s, i) in diff:
                 sc = float(corpora[names[s]][i].astype(np.float64) @ q[b].astype(np.float64))
                 assert abs(sc - kth) <= 1e-5 * abs(kth), f"query {b}: id {(s, i)} differs and is not a tie"
+    assert 0.1 < got_mask.mean() < 0.9, "smoke router routes nothing / everything: the search is not exercised"
     st = {n: sources[n].stats() for n in names}
     print("smoke ok: routed top-%d over %s, mask density %.2f, exact rescans %s" %
           (k, names, got_mask.mean(), {n: st[n]["exact_rescans"] for n in names}))
