@@ -341,12 +341,16 @@ def gpu_main(args, rows, workload):
     qps_e2e = B * args.steps / (e2e_run["ms_total"] * 1e-3)
     # rank 0's scan kernels: algorithmic bytes (rows * d_pad * 2, the bf16 plane once per pass) / event time
     achieved = dev_run["scan_bytes"] / max(dev_run["scan_ms"], 1e-9) * 1e-6 if dev_run["scan_launches"] else None
-    traffic = None
+    # DRAM traffic per launch: the ncu --set full capture (profiles/scan_traffic.json) measured
+    # dram bytes / algorithmic bytes for this kernel; scale it to this run's launch size.
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(REPO, "profiles", "scan_traffic.json")) as f:
             tj = json.load(f)
-        if tj.get("workload") == workload and tj.get("n_gpus") == world:
-            traffic = tj.get("dram_bytes_per_launch")
+        if dev_run["scan_launches"]:
+            traffic = tj["dram_over_algorithmic"] * dev_run["scan_bytes"] / dev_run["scan_launches"]
+            traffic_src = ("ncu dram read+write / algorithmic bytes = %.5f (%s), scaled to this launch size"
+                           % (tj["dram_over_algorithmic"], tj["source"]))
     except Exception:  # noqa: BLE001
         pass
 
@@ -400,6 +404,7 @@ def gpu_main(args, rows, workload):
             "gpu_launches": dev_run["launches"],
             "roofline": {"bound": "hbm", "kernel": "rr_tc_scan_kernel", "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
                          "peak_source": peak_src, "launches_timed": dev_run["scan_launches"],
                          "kernel_share_of_step": dev_run["scan_ms"] / max(dev_run["ms_total"], 1e-9),
                          "algorithmic_bytes_per_launch": (dev_run["scan_bytes"] / dev_run["scan_launches"])
