@@ -729,6 +729,10 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
         h->kprime = (int)value;
     } else if (!strcmp(name, "profile")) {
         h->profile = value != 0;
+    } else if (!strcmp(name, "scan_path")) {
+        RR_REQUIRE(value == RR_PATH_AUTO || value == RR_PATH_SMALL || value == RR_PATH_GEMM,
+                   "scan_path must be 0 (auto), 1 (64-query passes) or 2 (large-batch kernel)");
+        h->scan_path = (int)value;
     } else {
         rr_set_error("rr_index_set_param: unknown parameter '%s'", name);
         return RR_ERR_INVALID;
@@ -769,17 +773,27 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
 
 static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// one chunk of <= RR_QCHUNK queries
+// Large-batch path: more than one 64-query pass and a dimension whose query tile fits TMEM.
+static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
+    if (!rr_gemm_scan_supported(h) || h->scan_path == RR_PATH_SMALL) return false;
+    if (h->scan_path == RR_PATH_GEMM) return true;
+    return nq > RR_TC_MAX_QTILE;
+}
+
+// one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch path) queries
 static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const uint8_t* mask_dev,
                            int64_t mask_stride, float* D_dev, int64_t* I_dev, int64_t out_stride,
                            cudaStream_t stream) {
     const int qt = rr_tc_scan_qtile(h);  // 0: tc path unavailable for this d
-    const bool use_tc = (h->mode == RR_MODE_AUTO) && qt > 0 && h->n > 0;
-    const int nq_pad = (int)rr_align_up((size_t)nq, RR_TC_MAX_QTILE);
+    const bool use_gemm = (h->mode == RR_MODE_AUTO) && h->n > 0 && rr_use_gemm_path(h, nq);
+    const bool use_tc = (h->mode == RR_MODE_AUTO) && qt > 0 && h->n > 0 && !use_gemm;
+    const int nq_pad = (int)rr_align_up((size_t)nq, use_gemm ? RR_GEMM_QTILE : RR_TC_MAX_QTILE);
     const int g_exact = h->sm_count * 2;
     const int64_t cand_stride =
-        std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
-                          (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH);
+        use_gemm ? std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
+                                     (int64_t)rr_gemm_scan_max_lists(h) * RR_GEMM_LIST_DEPTH)
+                 : std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
+                                     (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH);
 
     // carve the scratch block
     size_t off = 0;
@@ -814,7 +828,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
     rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, mask_dev, mask_stride,
                                                        qbf, qnorm, active, fail_flags, fail_list, ctl,
-                                                       use_tc ? 0 : 1);
+                                                       (use_tc || use_gemm) ? 0 : 1);
     RR_CUDA_CHECK(cudaGetLastError());
     rr_count_launch(1);
 
@@ -840,8 +854,32 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     fa.fail_list = fail_list;
     fa.ctl = ctl;
     fa.nfail_total = h->d_nfail_total;
-    fa.pad_inactive = use_tc ? 0 : 1;
+    fa.pad_inactive = (use_tc || use_gemm) ? 0 : 1;
 
+    if (use_gemm) {
+        // one launch covers the whole chunk: queries stationary in TMEM, corpus read once
+        const bool prof = h->profile != 0 && h->ev_used + 2 <= rr_index::kEvPool;
+        if (prof) {
+            for (int i = 0; i < 2; ++i)
+                if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
+            RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
+        }
+        int n_lists = 0;
+        int rc = rr_gemm_scan_launch(h, qbf, nq, active, &ctl->any_active, cand_s, cand_r, cand_stride, &n_lists,
+                                     prof ? reinterpret_cast<unsigned long long*>(h->d_nfail_total + 2) : nullptr,
+                                     stream);
+        if (rc != RR_OK) return rc;
+        rr_count_launch(1);
+        if (prof) {
+            RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
+            h->ev_used += 2;
+        }
+        fa.n_lists = n_lists;
+        fa.depth = RR_GEMM_LIST_DEPTH;
+        rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
+    }
     if (use_tc) {
         for (int p0 = 0; p0 < nq; p0 += qt) {
             const int nqt = std::min(qt, nq - p0);
@@ -862,7 +900,6 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
             rr_count_launch(1);
             if (prof) {
                 RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
-                h->ev_bytes[h->ev_used / 2] = h->n * (int64_t)h->d_pad * 2;
                 h->ev_used += 2;
             }
             fa.n_lists = n_lists;
@@ -919,8 +956,9 @@ extern "C" int rr_index_search_ex(rr_index_t* h, const float* q_dev, int64_t nq,
     RR_REQUIRE(out_stride >= k, "rr_index_search: out_stride < k");
     rr_device_guard g(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    for (int64_t q0 = 0; q0 < nq; q0 += RR_QCHUNK) {
-        const int nqc = (int)std::min<int64_t>(RR_QCHUNK, nq - q0);
+    const int64_t chunk = (h->mode == RR_MODE_AUTO && rr_use_gemm_path(h, nq)) ? RR_GEMM_QCHUNK : RR_QCHUNK;
+    for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+        const int nqc = (int)std::min<int64_t>(chunk, nq - q0);
         int rc = rr_search_chunk(h, q_dev + (size_t)q0 * h->d, nqc, k,
                                  mask_dev ? mask_dev + q0 * mask_stride : nullptr, mask_stride,
                                  D_dev + (size_t)q0 * out_stride, I_dev + (size_t)q0 * out_stride, out_stride,

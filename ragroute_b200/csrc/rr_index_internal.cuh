@@ -15,7 +15,12 @@ constexpr int RR_TC_LIST_DEPTH = 16;   // entries per (epilogue warp, query) lis
 constexpr int RR_TC_EPI_WARPS = 4;
 constexpr int RR_EXACT_LIST_DEPTH = 32;
 constexpr int RR_EXACT_WARPS = 8;
-constexpr int RR_QCHUNK = 256;         // queries handled per internal chunk
+constexpr int RR_QCHUNK = 256;         // queries handled per internal chunk (64-query scan passes)
+constexpr int RR_GEMM_TILE_ROWS = 128; // corpus rows per MMA in the large-batch kernel (UMMA N)
+constexpr int RR_GEMM_QTILE = 128;     // queries per CTA in the large-batch kernel (UMMA M, TMEM lanes)
+constexpr int RR_GEMM_LIST_DEPTH = 32; // entries per (CTA, query) list of the large-batch kernel
+constexpr int RR_GEMM_QCHUNK = 1024;   // queries per chunk on the large-batch path
+constexpr int RR_PATH_AUTO = 0, RR_PATH_SMALL = 1, RR_PATH_GEMM = 2;  // set_param "scan_path"
 constexpr int RR_EXACT_MAX_QSUB = 16;  // queries per exact-scan launch
 
 struct rr_index {
@@ -34,6 +39,7 @@ struct rr_index {
     int mode = RR_MODE_AUTO;
     int kprime = 128;
     int profile = 0;
+    int scan_path = RR_PATH_AUTO;
 
     // per-search scratch (grow-only)
     void* scratch = nullptr;
@@ -52,7 +58,6 @@ struct rr_index {
     static constexpr int kEvPool = 4096;  // 2048 timed launches between two rr_index_get_stats calls
     cudaEvent_t ev_pool[kEvPool] = {};
     int ev_used = 0;
-    int64_t ev_bytes[kEvPool / 2] = {};
 };
 
 // rr_scan_tc.cu: launch the tcgen05 scan for one pass of <= qtile queries: rows
@@ -68,3 +73,16 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
 int rr_tc_scan_num_lists(const rr_index* h);
 // queries per pass for this dimension (stationary query tile must fit in smem)
 int rr_tc_scan_qtile(const rr_index* h);
+
+// rr_tma_host.cu: 2-D tensor map over a row-major bf16 matrix [rows, d_pad]; box = 64 columns
+// (one 128-byte swizzle row) x box_rows rows, SWIZZLE_128B.
+int rr_make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int d_pad, int box_rows);
+
+// rr_scan_gemm.cu: large-batch scan (queries stationary in TMEM).  qbf16 holds
+// ceil(nq / 128) * 128 zero-padded rows; active has as many entries.  Produces one list of
+// RR_GEMM_LIST_DEPTH entries per (corpus slice, query); *n_lists_out = number of slices.
+bool rr_gemm_scan_supported(const rr_index* h);
+int rr_gemm_scan_max_lists(const rr_index* h);
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, const uint8_t* active_dev,
+                        const int* any_active_dev, float* cand_s, uint32_t* cand_r, int64_t cand_stride,
+                        int* n_lists_out, unsigned long long* bytes_scanned_dev, cudaStream_t stream);

@@ -1,0 +1,366 @@
+// The scoring pass for LARGE query batches (more than one 64-query pass):
+// scores = Q_bf16 . X_bf16^T with the QUERIES as the stationary operand.
+// Replaces the arithmetic of faiss IndexFlatIP::search
+// (/root/reference/ragroute/data_source.py:158,186,203) for batched callers, up to the
+// exact rescoring done in rr_index.cu.
+//
+// With B >= 128 queries the arithmetic intensity over the bf16 plane (B flop/byte)
+// approaches / exceeds the ridge (~215), so the corpus must be read from HBM once per
+// chunk of up to 1024 queries and every byte brought into an SM must be used against as
+// many queries as possible:
+//   * a tile of 128 queries lives in TENSOR MEMORY for the whole kernel as the UMMA A
+//     operand (TS form of tcgen05.mma: row m of A in TMEM lane m, 2 bf16 per 32-bit
+//     column; 768 dims = 384 columns), written once by tcgen05.st;
+//   * corpus rows stream through shared memory as the B operand, 128 rows x 64 k per
+//     16 KB TMA stage (128B swizzle), ring of 12 stages (192 KB in flight per SM); UMMA
+//     N = 128 because one tcgen05.mma costs >= 45 cycles whatever its N (measured:
+//     scripts/microbench/umma_rate.cu), so N = 64 would waste 30 % of the tensor pipe;
+//   * the remaining TMEM columns hold 1-3 accumulator stages of 128 fp32 columns
+//     (128 queries x 128 corpus rows each);
+//   * epilogue orientation: TMEM lane = query, so every epilogue THREAD owns one query:
+//     its running threshold sits in a register and the 128 scores of a tile cost one max
+//     tree + one compare.  Survivors are inserted WARP-COOPERATIVELY into that query's
+//     unsorted top-32 list in shared memory (lane e holds entry e; replace-the-minimum
+//     with three redux.sync), about 40 cycles per insert and no divergence -- a per-thread
+//     sorted insert measured ~2000 cycles and made the epilogue the bottleneck.
+// CTA c works on query tile (c % nqt) and corpus slice (c / nqt): the nqt CTAs that share
+// a slice stream the same rows at the same time, so HBM is read once and the other
+// nqt - 1 reads hit L2.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = A loader + epilogue.
+#include <algorithm>
+
+#include "rr_index_internal.cuh"
+#include "rr_ptx.cuh"
+#include "rr_topm.cuh"
+
+namespace {
+using namespace rr_ptx;
+
+constexpr int kNT = RR_GEMM_TILE_ROWS;               // corpus rows per MMA (UMMA N)
+constexpr int kStageBytes = kNT * RR_TC_KCHUNK * 2;  // 16 KB
+constexpr int kDepth = RR_GEMM_LIST_DEPTH;
+constexpr int kQTile = RR_GEMM_QTILE;  // 128 queries = TMEM lanes
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 12;
+constexpr int kMaxAcc = 3;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr uint32_t kTmemCols = 512;
+
+struct GemmParams {
+    int64_t n_rows;
+    int n_tiles;     // ceil(n_rows / kNT)
+    int num_kc;      // d_pad / 64
+    int d_pad;
+    int nq;          // valid queries in the chunk
+    int nqt;         // query tiles of 128
+    int n_slices;    // corpus slices = gridDim.x / nqt
+    int stages;
+    int acc_stages;
+    uint64_t l2_hint;
+    const uint16_t* qbf16;  // [nqt * 128][d_pad] bf16, zero padded
+    const uint8_t* active;  // [nqt * 128]
+    const int* any_active;
+    unsigned long long* bytes_scanned;
+    float* cand_s;  // [query][slice][kDepth]
+    uint32_t* cand_r;
+    int64_t cand_stride;
+};
+
+// Warp-cooperative insert of (v, row) into the unsorted top-kDepth list of one query
+// (entries at lsp[0..31], lane e owns entry e): the worst entry -- lowest score, then
+// highest row; an empty slot is (-inf, RR_NO_ROW) and therefore always worst -- is
+// replaced.  Returns the list's new minimum score = the query's new threshold (-inf
+// while an empty slot remains).  The caller guarantees v > current minimum.
+__device__ __forceinline__ float coop_insert(float* lsp, uint32_t* lrp, float v, uint32_t row, int lane) {
+    static_assert(kDepth == 32, "one list entry per lane");
+    const float es = lsp[lane];
+    const uint32_t er = lrp[lane];
+    uint32_t key = rr_float_key(es);
+    const uint32_t kmin = __reduce_min_sync(RR_FULL, key);
+    const uint32_t rmax = __reduce_max_sync(RR_FULL, (key == kmin) ? er : 0u);
+    const unsigned cand = __ballot_sync(RR_FULL, key == kmin && er == rmax);
+    if (lane == __ffs(cand) - 1) {
+        lsp[lane] = v;
+        lrp[lane] = row;
+        key = rr_float_key(v);
+    }
+    __syncwarp();
+    return rr_key_float(__reduce_min_sync(RR_FULL, key));
+}
+
+// One column of the tile: lanes whose score beats their own threshold hand it to the warp.
+// Out of line: it runs for a small fraction of the columns, and 128 inlined copies would not
+// fit the instruction cache.
+__device__ __noinline__ float epi_take(unsigned b, float v, uint32_t row, float thr, float* ls_w, uint32_t* lr_w,
+                                       int lane) {
+    while (b) {
+        const int src = __ffs(b) - 1;
+        b &= b - 1;
+        const float cv = __shfl_sync(RR_FULL, v, src);
+        const float nt = coop_insert(ls_w + src * kDepth, lr_w + src * kDepth, cv, row, lane);
+        if (lane == src) thr = nt;
+    }
+    return thr;
+}
+static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA box of the hi plane");
+
+__global__ void __launch_bounds__(kThreads, 1)
+rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+    if (*p.any_active == 0) return;  // no query routed to this source: do not touch the corpus
+    if (p.bytes_scanned && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd(p.bytes_scanned, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
+
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
+                                               ~(uintptr_t)1023);
+    uint8_t* x_sm = base;
+    float* ls = reinterpret_cast<float*>(x_sm + p.stages * kStageBytes);  // [128 queries][kDepth]
+    uint32_t* lr = reinterpret_cast<uint32_t*>(ls + kDepth * kQTile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lr + kDepth * kQTile);
+    uint64_t* bar_full = bars;
+    uint64_t* bar_empty = bars + kMaxStages;
+    uint64_t* bar_acc_full = bars + 2 * kMaxStages;
+    uint64_t* bar_acc_empty = bar_acc_full + kMaxAcc;
+    uint64_t* bar_a = bar_acc_empty + kMaxAcc;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qt = blockIdx.x % p.nqt;
+    const int slice = blockIdx.x / p.nqt;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_x);
+        for (int i = 0; i < p.stages; ++i) {
+            mbar_init(smem_u32(bar_full + i), 1);
+            mbar_init(smem_u32(bar_empty + i), 1);
+        }
+        for (int i = 0; i < p.acc_stages; ++i) {
+            mbar_init(smem_u32(bar_acc_full + i), 1);
+            mbar_init(smem_u32(bar_acc_empty + i), 4);
+        }
+        mbar_init(smem_u32(bar_a), 4);
+        fence_barrier_init();
+    } else if (warp == 1) {
+        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t a_cols = (uint32_t)p.num_kc * 32u;  // d_pad / 2
+    const uint32_t acc_base = tmem_base + a_cols;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+                for (int kc = 0; kc < p.num_kc; ++kc) {
+                    mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+                    mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
+                    tma_load_2d(smem_u32(x_sm + stage * kStageBytes), &tmap_x, smem_u32(bar_full + stage),
+                                kc * RR_TC_KCHUNK, tile * kNT, p.l2_hint);
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =======================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kNT);
+            mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM
+            tc_fence_after();
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+                mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
+                for (int kc = 0; kc < p.num_kc; ++kc) {
+                    mbar_wait(smem_u32(bar_full + stage), phase);
+                    tc_fence_after();
+                    const uint32_t b_addr = smem_u32(x_sm + stage * kStageBytes);
+#pragma unroll
+                    for (int k = 0; k < RR_TC_KCHUNK / 16; ++k) {
+                        umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((kc * 4 + k) * 8), umma_desc_sw128(b_addr + k * 32),
+                                     idesc, (uint32_t)((kc | k) != 0));
+                    }
+                    umma_commit(smem_u32(bar_empty + stage));
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(smem_u32(bar_acc_full + acc));
+                if (++acc == p.acc_stages) {
+                    acc = 0;
+                    acc_phase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ============ warps 2..5: load the query tile into TMEM, then epilogue ============
+        const int quad = warp & 3;           // TMEM lanes [32*quad, 32*quad+32) are this warp's
+        const int t = quad * 32 + lane;      // query row inside the tile = TMEM lane
+        const int qg = qt * kQTile + t;      // query inside the chunk
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
+        {
+            const uint4* src = reinterpret_cast<const uint4*>(p.qbf16 + (size_t)qg * p.d_pad);
+            for (uint32_t c = 0; c < a_cols; c += 8) {
+                const uint4 v0 = __ldg(src + (c >> 2));
+                const uint4 v1 = __ldg(src + (c >> 2) + 1);
+                const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                tmem_st_x8(lane_addr + c, r);
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bar_a));
+        }
+        float* ls_w = ls + quad * 32 * kDepth;  // this warp's 32 lists, [query][entry]
+        uint32_t* lr_w = lr + quad * 32 * kDepth;
+        for (int i = lane; i < 32 * kDepth; i += 32) {
+            ls_w[i] = RR_NEG_INF;
+            lr_w[i] = RR_NO_ROW;
+        }
+        __syncwarp();
+        const bool act = (qg < p.nq) && (p.active[qg] != 0);
+        float thr = act ? RR_NEG_INF : __builtin_huge_valf();
+
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+            mbar_wait(smem_u32(bar_acc_full + acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_acc = lane_addr + a_cols + (uint32_t)(acc * kNT);
+            uint32_t r[4][32];
+            tmem_ld_x32_nowait(t_acc, r[0]);
+            tmem_ld_x32_nowait(t_acc + 32, r[1]);
+            tmem_ld_x32_nowait(t_acc + 64, r[2]);
+            tmem_ld_x32_nowait(t_acc + 96, r[3]);
+            tmem_ld_wait();
+            // the registers hold the tile: hand the accumulator back before selecting
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(bar_acc_empty + acc));
+            if (++acc == p.acc_stages) {
+                acc = 0;
+                acc_phase ^= 1u;
+            }
+            const int64_t row0 = (int64_t)tile * kNT;
+            if (row0 + kNT > p.n_rows) {  // last, partial tile: rows past the end never qualify
+                const int valid = (int)(p.n_rows - row0);
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c * 32 + j >= valid) r[c][j] = __float_as_uint(RR_NEG_INF);
+            }
+            // maxima of the 16 groups of 8 columns, then of the tile: hits are sparse (a few
+            // per warp and tile), so whole groups are skipped with one vote each
+            float m8[16];
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                const uint32_t* rg = &r[g >> 2][(g & 3) * 8];
+                const float a0 = fmaxf(__uint_as_float(rg[0]), __uint_as_float(rg[1]));
+                const float a1 = fmaxf(__uint_as_float(rg[2]), __uint_as_float(rg[3]));
+                const float a2 = fmaxf(__uint_as_float(rg[4]), __uint_as_float(rg[5]));
+                const float a3 = fmaxf(__uint_as_float(rg[6]), __uint_as_float(rg[7]));
+                m8[g] = fmaxf(fmaxf(a0, a1), fmaxf(a2, a3));
+            }
+            float mx = m8[0];
+#pragma unroll
+            for (int g = 1; g < 16; ++g) mx = fmaxf(mx, m8[g]);
+            if (__any_sync(RR_FULL, mx > thr)) {
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    if (__any_sync(RR_FULL, m8[g] > thr)) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float v = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
+                            const unsigned hb = __ballot_sync(RR_FULL, v > thr);
+                            if (hb) thr = epi_take(hb, v, (uint32_t)(row0 + g * 8 + j), thr, ls_w, lr_w, lane);
+                        }
+                    }
+                }
+            }
+        }
+        // publish sorted: [query][list = slice][kDepth], lane e writes entry e
+        for (int i = 0; i < 32; ++i) {
+            const int qi = qt * kQTile + quad * 32 + i;
+            if (qi >= p.nq) break;
+            float es = ls_w[i * kDepth + lane];
+            uint32_t er = lr_w[i * kDepth + lane];
+            rr_warp_sort(es, er, lane);
+            const int64_t o = (int64_t)qi * p.cand_stride + (int64_t)slice * kDepth + lane;
+            p.cand_s[o] = es;
+            p.cand_r[o] = er;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+}  // namespace
+
+bool rr_gemm_scan_supported(const rr_index* h) {
+    // the query tile (d_pad / 2 TMEM columns) must leave room for one 128-column accumulator
+    return h->d_pad / 2 + kNT <= (int)kTmemCols;
+}
+
+int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
+
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, const uint8_t* active_dev,
+                        const int* any_active_dev, float* cand_s, uint32_t* cand_r, int64_t cand_stride,
+                        int* n_lists_out, unsigned long long* bytes_scanned_dev, cudaStream_t stream) {
+    RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
+    RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
+    if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
+        int rc = rr_make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, kNT);
+        if (rc != RR_OK) return rc;
+        h->tmap_hi_ptr = h->hi;
+        h->tmap_hi_rows = h->n;
+    }
+    GemmParams p;
+    p.n_rows = h->n;
+    p.n_tiles = (int)((h->n + kNT - 1) / kNT);
+    p.num_kc = h->d_pad / RR_TC_KCHUNK;
+    p.d_pad = h->d_pad;
+    p.nq = nq;
+    p.nqt = (nq + kQTile - 1) / kQTile;
+    p.n_slices = std::max(1, std::min(h->sm_count / p.nqt, p.n_tiles));
+    p.acc_stages = std::min(kMaxAcc, ((int)kTmemCols - h->d_pad / 2) / kNT);
+    const size_t fixed = 1024 + (size_t)kDepth * kQTile * 8 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
+    p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / kStageBytes);
+    const size_t smem = fixed + (size_t)p.stages * kStageBytes;
+    // sibling CTAs (other query tiles, same slice) re-read each tile from L2 right away
+    p.l2_hint = (p.nqt > 1) ? kTmaEvictNormal : kTmaEvictFirst;
+    p.qbf16 = qbf16_dev;
+    p.active = active_dev;
+    p.any_active = any_active_dev;
+    p.bytes_scanned = bytes_scanned_dev;
+    p.cand_s = cand_s;
+    p.cand_r = cand_r;
+    p.cand_stride = cand_stride;
+    RR_REQUIRE((int64_t)p.n_slices * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemLimit));
+        attr_done[h->device & 63] = true;
+    }
+    *n_lists_out = p.n_slices;
+    rr_gemm_scan_kernel<<<p.n_slices * p.nqt, kThreads, smem, stream>>>(h->tmap_hi, p);
+    RR_CUDA_CHECK(cudaGetLastError());
+    return RR_OK;
+}

@@ -22,6 +22,7 @@
 #include <algorithm>
 
 #include "rr_index_internal.cuh"
+#include "rr_ptx.cuh"
 #include "rr_topm.cuh"
 
 namespace {
@@ -50,114 +51,7 @@ struct TcParams {
     int64_t cand_stride;
 };
 
-// ------------------------------------------------------------- PTX wrappers --
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    return ok;
-}
-// Bounded wait: a pipeline-protocol bug must trap (reported as a CUDA error), never
-// hang the device.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 8000000000ll) __trap();  // ~4 s at 2 GHz
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0,
-                                            int c1, uint64_t hint) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        :
-        : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
-        : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() {
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tc_fence_after() {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_smem),
-                 "r"(ncols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by one thread
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
-                                          uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        :
-        : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32"
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
-          "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor, K-major operand, 128B swizzle, rows of 128 bytes,
-// 8-row groups 1024 bytes apart (cute::UMMA::SmemDescriptor: start>>4 [0,14),
-// LBO>>4 [16,30) = 1 (unused with swizzle), SBO>>4 [32,46) = 64, version [46,48) = 1,
-// layout_type [61,64) = 2 (SWIZZLE_128B)).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
-           (2ull << 61);
-}
-// UMMA instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 = 1 @4,
-// a_format BF16 = 1 @7, b_format BF16 = 1 @10, a/b K-major (bits 15,16 = 0),
-// N>>3 @17, M>>4 @24.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
+using namespace rr_ptx;
 
 // Candidate handling for one (epilogue warp, query): `b` = lanes whose score beats
 // the list's current tail.  Kept out of line: it runs for a small fraction of the
@@ -380,44 +274,6 @@ rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
 // ------------------------------------------------------------------ host ----
 
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
-                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
-                                    CUtensorMapFloatOOBfill);
-
-PFN_encodeTiled get_encode_fn() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-    return fn;
-}
-
-int make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int d_pad, int box_rows) {
-    PFN_encodeTiled enc = get_encode_fn();
-    if (!enc) {
-        rr_set_error("cuTensorMapEncodeTiled is not available from the driver");
-        return RR_ERR_CUDA;
-    }
-    cuuint64_t gdim[2] = {(cuuint64_t)d_pad, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)d_pad * 2};
-    cuuint32_t box[2] = {(cuuint32_t)RR_TC_KCHUNK, (cuuint32_t)box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        rr_set_error("cuTensorMapEncodeTiled failed (CUresult %d) rows=%lld d_pad=%d box_rows=%d", (int)r,
-                     (long long)rows, d_pad, box_rows);
-        return RR_ERR_CUDA;
-    }
-    return RR_OK;
-}
-
 struct SmemPlan {
     int stages;
     size_t bytes;
@@ -469,13 +325,13 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
     const SmemPlan pl = plan_smem(h->d_pad, qt);
     RR_REQUIRE(pl.stages >= 2, "rr_tc_scan_launch: shared memory plan failed for d_pad=%d", h->d_pad);
     if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
-        int rc = make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, RR_TC_TILE_ROWS);
+        int rc = rr_make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, RR_TC_TILE_ROWS);
         if (rc != RR_OK) return rc;
         h->tmap_hi_ptr = h->hi;
         h->tmap_hi_rows = h->n;
     }
     alignas(64) CUtensorMap tq;
-    int rc = make_tmap_bf16_rows(&tq, qbf16_dev, q_rows_total, h->d_pad, qt);
+    int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, q_rows_total, h->d_pad, qt);
     if (rc != RR_OK) return rc;
 
     TcParams p;

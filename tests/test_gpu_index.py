@@ -233,3 +233,64 @@ def test_errors_like_faiss(faiss):
     from ragroute_b200._lib import RRError
     with pytest.raises(RRError):
         ix.search(np.ones((1, 8), dtype=np.float32), 33)    # k > RR_MAX_K: loud, not silent
+
+
+# ---------------------------------------------------------------------------
+# Large-batch path (rr_scan_gemm.cu: queries stationary in TMEM).  "scan_path" 2
+# forces it for any batch size so that small cases reach it too.
+# ---------------------------------------------------------------------------
+def _gemm_index(faiss, xb):
+    ix = _index(faiss, xb, "auto")
+    ix.set_param("scan_path", 2)
+    return ix
+
+
+@pytest.mark.parametrize("n,d,k,nq", [(5000, 768, 32, 5), (20000, 768, 32, 130), (4000, 384, 10, 64),
+                                      (2500, 100, 7, 2), (63, 768, 32, 3), (9000, 512, 10, 257)])
+def test_gemm_path_vs_oracle(faiss, n, d, k, nq):
+    rng = np.random.default_rng(n + d + nq)
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    ix = _gemm_index(faiss, xb)
+    D, I = ix.search(q, k)
+    Dr, Ir = oracle.search(q, xb, k)
+    oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    De, Ie = _index(faiss, xb, "exact").search(q, k)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De), "gemm path and exact must agree bit for bit"
+
+
+def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
+    """On benign MedRAG-shaped data the certificate must pass for every query (otherwise
+    the exact rescan would hide a broken tensor-core kernel), for 1, 2 and 8 query tiles."""
+    d, k = 768, 32
+    xb = syn.corpus_rows(2, 70000, d)
+    for nq in (100, 256, 1024):
+        q = syn.queries(nq, d, [2], seed=nq)
+        ix = _gemm_index(faiss, xb)
+        D, I = ix.search(q, k)
+        assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data: {ix.stats()}"
+        ixs = _index(faiss, xb, "auto")
+        ixs.set_param("scan_path", 1)
+        Ds, Is = ixs.search(q, k)
+        assert ixs.stats()["exact_rescans"] == 0
+        assert np.array_equal(I, Is) and np.array_equal(D, Ds), "both tensor-core paths must agree bit for bit"
+        Dr, Ir = oracle.search(q[:40], xb, k)
+        oracle.compare_topk(D[:40], I[:40], Dr, Ir, x=q[:40], xb=xb)
+
+
+def test_gemm_path_mask_chunks_and_default_dispatch(faiss):
+    d, k = 768, 10
+    xb = syn.corpus_rows(1, 30000, d)
+    q = syn.queries(1100, d, [1], seed=12)     # > 1024: two chunks on the large-batch path
+    ix = _index(faiss, xb, "auto")             # default dispatch: nq > 64 takes the large-batch path
+    qt = torch.from_numpy(q).cuda()
+    mask = (torch.arange(1100, device="cuda") % 3 != 0).to(torch.uint8).reshape(-1, 1).contiguous()
+    D, I = ix.search_tensor(qt, k, mask=mask)
+    torch.cuda.synchronize()
+    D, I = D.cpu().numpy(), I.cpu().numpy()
+    assert ix.stats()["exact_rescans"] == 0
+    off = (np.arange(1100) % 3 == 0)
+    assert (I[off] == -1).all() and (D[off] == -FLT_MAX).all()
+    sel = np.nonzero(~off)[0][::37]
+    Dr, Ir = oracle.search(q[sel], xb, k)
+    oracle.compare_topk(D[sel], I[sel], Dr, Ir, x=q[sel], xb=xb)
