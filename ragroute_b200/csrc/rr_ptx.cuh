@@ -154,6 +154,20 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
         : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// one lane of a converged warp (warp-uniform control flow around it keeps the operands of
+// the single-thread instructions -- UTMALDG, UTCHMMA, UTCBAR -- in uniform registers)
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xFFFFFFFF;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+// constant upper part of umma_desc_sw128; the low 14 bits are (smem address >> 4), so a
+// 32-byte K-step inside a stage is "+ 2" on the descriptor
+constexpr uint64_t kUmmaDescSw128Hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 constexpr uint64_t kTmaEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kTmaEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kTmaEvictLast = 0x14F0000000000000ull;

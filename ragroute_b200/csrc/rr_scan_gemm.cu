@@ -151,56 +151,64 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
     const uint32_t a_cols = (uint32_t)p.num_kc * 32u;  // d_pad / 2
     const uint32_t acc_base = tmem_base + a_cols;
 
+    // Warps 0 and 1 run their loops converged (all 32 lanes wait on the barriers) and elect one
+    // lane for the single-thread instructions: with warp-uniform control flow the compiler keeps
+    // addresses and descriptors in uniform registers -- an `if (lane == 0)` loop costs ~150
+    // issue cycles per MMA (measured) and makes the issuing thread the bottleneck.
     if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
-                for (int kc = 0; kc < p.num_kc; ++kc) {
-                    mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t x_base = smem_u32(x_sm);
+        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+            for (int kc = 0; kc < p.num_kc; ++kc) {
+                mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
-                    tma_load_2d(smem_u32(x_sm + stage * kStageBytes), &tmap_x, smem_u32(bar_full + stage),
+                    tma_load_2d(x_base + stage * kStageBytes, &tmap_x, smem_u32(bar_full + stage),
                                 kc * RR_TC_KCHUNK, tile * kNT, p.l2_hint);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                }
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =======================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kNT);
-            mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM
+        // ===================== MMA issuer =======================
+        constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kNT);
+        mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM
+        tc_fence_after();
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint32_t x_base = smem_u32(x_sm);
+        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+            mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
             tc_fence_after();
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
-                mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
+            const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
+            for (int kc = 0; kc < p.num_kc; ++kc) {
+                mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
-                for (int kc = 0; kc < p.num_kc; ++kc) {
-                    mbar_wait(smem_u32(bar_full + stage), phase);
-                    tc_fence_after();
-                    const uint32_t b_addr = smem_u32(x_sm + stage * kStageBytes);
-#pragma unroll
-                    for (int k = 0; k < RR_TC_KCHUNK / 16; ++k) {
-                        umma_bf16_ts(d_tmem, tmem_base + (uint32_t)((kc * 4 + k) * 8), umma_desc_sw128(b_addr + k * 32),
-                                     idesc, (uint32_t)((kc | k) != 0));
-                    }
-                    umma_commit(smem_u32(bar_empty + stage));
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageBytes) >> 4) & 0x3FFFu);
+                const uint32_t a_tmem = tmem_base + (uint32_t)(kc * 32);
+                if (elect_one_sync()) {
+                    umma_bf16_ts(d_tmem, a_tmem, b_desc, idesc, (uint32_t)(kc != 0));
+                    umma_bf16_ts(d_tmem, a_tmem + 8, b_desc + 2, idesc, 1u);
+                    umma_bf16_ts(d_tmem, a_tmem + 16, b_desc + 4, idesc, 1u);
+                    umma_bf16_ts(d_tmem, a_tmem + 24, b_desc + 6, idesc, 1u);
+                    umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
+                    if (kc == p.num_kc - 1) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
                 }
-                umma_commit(smem_u32(bar_acc_full + acc));
-                if (++acc == p.acc_stages) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
+            }
+            if (++acc == p.acc_stages) {
+                acc = 0;
+                acc_phase ^= 1u;
             }
         }
     } else {

@@ -33,8 +33,8 @@ constexpr int kThreads = 192;
 constexpr int kMaxStages = 8;
 constexpr int kSmemLimit = 227 * 1024;
 constexpr int kDepth = RR_TC_LIST_DEPTH;
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
+constexpr uint64_t kEvictFirst = rr_ptx::kTmaEvictFirst;
+constexpr uint64_t kEvictLast = rr_ptx::kTmaEvictLast;
 
 struct TcParams {
     int64_t n_rows;
@@ -140,61 +140,71 @@ rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Warps 0 and 1 run their loops converged and elect one lane for the single-thread
+    // instructions, so that addresses and descriptors stay in uniform registers (an
+    // `if (lane == 0)` loop costs ~150 issue cycles per MMA and caps the scan below HBM speed).
     if (warp == 0) {
-        // ===================== TMA producer (one thread) =====================
-        if (lane == 0) {
+        // ===================== TMA producer =====================
+        const uint32_t x_base = smem_u32(x_sm);
+        if (elect_one_sync()) {
             mbar_arrive_expect_tx(smem_u32(bar_q), (uint32_t)q_bytes);
             for (int kc = 0; kc < p.num_kc; ++kc)
                 tma_load_2d(smem_u32(q_sm + kc * QT * 128), &tmap_q, smem_u32(bar_q), kc * RR_TC_KCHUNK,
                             p.q_row0, kEvictLast);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int kc = 0; kc < p.num_kc; ++kc) {
-                    mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            for (int kc = 0; kc < p.num_kc; ++kc) {
+                mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+                if (elect_one_sync()) {
                     mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
-                    tma_load_2d(smem_u32(x_sm + stage * kStageBytes), &tmap_x, smem_u32(bar_full + stage),
+                    tma_load_2d(x_base + stage * kStageBytes, &tmap_x, smem_u32(bar_full + stage),
                                 kc * RR_TC_KCHUNK, tile * RR_TC_TILE_ROWS, kEvictFirst);
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                }
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer (one thread) =======================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(RR_TC_TILE_ROWS, QT);
-            mbar_wait(smem_u32(bar_q), 0);
+        // ===================== MMA issuer =======================
+        constexpr uint32_t idesc = umma_idesc_bf16(RR_TC_TILE_ROWS, QT);
+        mbar_wait(smem_u32(bar_q), 0);
+        tc_fence_after();
+        int stage = 0, acc = 0;
+        uint32_t phase = 0, acc_phase = 0;
+        const uint32_t x_base = smem_u32(x_sm);
+        const uint32_t q_base = smem_u32(q_sm);
+        for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
             tc_fence_after();
-            int stage = 0, acc = 0;
-            uint32_t phase = 0, acc_phase = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * QT);
+            for (int kc = 0; kc < p.num_kc; ++kc) {
+                mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * QT);
-                for (int kc = 0; kc < p.num_kc; ++kc) {
-                    mbar_wait(smem_u32(bar_full + stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(x_sm + stage * kStageBytes);
-                    const uint32_t b_addr = smem_u32(q_sm + kc * QT * 128);
-#pragma unroll
-                    for (int k = 0; k < RR_TC_KCHUNK / 16; ++k) {
-                        umma_bf16(d_tmem, umma_desc_sw128(a_addr + k * 32), umma_desc_sw128(b_addr + k * 32),
-                                  idesc, (uint32_t)((kc | k) != 0));
-                    }
+                const uint64_t a_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageBytes) >> 4) & 0x3FFFu);
+                const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((q_base + kc * QT * 128) >> 4) & 0x3FFFu);
+                if (elect_one_sync()) {
+                    umma_bf16(d_tmem, a_desc, b_desc, idesc, (uint32_t)(kc != 0));
+                    umma_bf16(d_tmem, a_desc + 2, b_desc + 2, idesc, 1u);
+                    umma_bf16(d_tmem, a_desc + 4, b_desc + 4, idesc, 1u);
+                    umma_bf16(d_tmem, a_desc + 6, b_desc + 6, idesc, 1u);
                     umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
-                    if (++stage == p.stages) {
-                        stage = 0;
-                        phase ^= 1u;
-                    }
+                    if (kc == p.num_kc - 1) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator -> epilogue
                 }
-                umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete -> epilogue
-                if (++acc == kAccStages) {
-                    acc = 0;
-                    acc_phase ^= 1u;
+                __syncwarp();
+                if (++stage == p.stages) {
+                    stage = 0;
+                    phase ^= 1u;
                 }
+            }
+            if (++acc == kAccStages) {
+                acc = 0;
+                acc_phase ^= 1u;
             }
         }
     } else {
