@@ -116,6 +116,7 @@ typedef struct rr_index_stats {
     int64_t scan_launches;     /* bf16 scan kernel launches that were timed      */
     double scan_ms_total;      /* their summed CUDA-event time (profile = 1)     */
     int64_t scan_bytes_total;  /* algorithmic bytes they covered: rows * d_pad*2 */
+    int64_t scan_flops_total;  /* algorithmic flops: 2 * routed queries * rows * d_pad */
 } rr_index_stats;
 /* Synchronises the recorded events; resets the timing fields when reset != 0. */
 int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset);

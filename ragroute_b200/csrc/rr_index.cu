@@ -93,11 +93,28 @@ rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
     }
 }
 
-// Control block of one query chunk (device memory, zeroed per chunk).
-struct rr_chunk_ctl {
-    int n_fail;      // queries needing the exact path
-    int any_active;  // at least one query is routed to this source
-};
+// Large-batch path: compact the ROUTED queries of a chunk (<= 1024) to the front.  cpos[b] = row of
+// query b in the bf16 query buffer: routed queries keep their order in [0, n_active), unrouted ones
+// follow in [n_active, nq) (their rows are zero).  One block of 1024 threads.
+__global__ void __launch_bounds__(1024)
+rr_compact_queries_kernel(const uint8_t* __restrict__ mask, int64_t mask_stride, int nq, int* __restrict__ cpos,
+                          rr_chunk_ctl* ctl) {
+    __shared__ int warp_cnt[32];
+    const int b = threadIdx.x, lane = b & 31, w = b >> 5;
+    const bool act = (b < nq) && (mask ? (mask[(int64_t)b * mask_stride] != 0) : true);
+    const unsigned bal = __ballot_sync(RR_FULL, act);
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+    for (int i = 0; i < 32; ++i) {
+        const int c = warp_cnt[i];
+        if (i < w) before += c;
+        total += c;
+    }
+    before += __popc(bal & ((1u << lane) - 1u));
+    if (b < nq) cpos[b] = act ? before : total + (b - before);
+    if (b == 0) ctl->n_active = total;
+}
 
 // fp32 queries -> bf16 tile rows (zero padded to d_pad; rows >= nq zeroed), norms,
 // activity flags.  grid = nq_pad blocks.
@@ -106,9 +123,11 @@ rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
                        const uint8_t* __restrict__ mask, int64_t mask_stride,
                        uint16_t* __restrict__ qbf16, float* __restrict__ qnorm,
                        uint8_t* __restrict__ active, uint8_t* __restrict__ fail_flags,
-                       int* __restrict__ fail_list, rr_chunk_ctl* ctl, int exact_all) {
+                       int* __restrict__ fail_list, rr_chunk_ctl* ctl, int exact_all,
+                       const int* __restrict__ cpos) {
     const int b = blockIdx.x;
-    uint16_t* out = qbf16 + (int64_t)b * d_pad;
+    // large-batch path: routed queries are compacted to the front of the bf16 buffer
+    uint16_t* out = qbf16 + (int64_t)((cpos && b < nq) ? cpos[b] : b) * d_pad;
     if (b >= nq) {
         for (int e = threadIdx.x; e < d_pad; e += blockDim.x) out[e] = 0;
         if (threadIdx.x == 0) active[b] = 0;
@@ -287,6 +306,8 @@ struct rr_finalize_args {
     rr_chunk_ctl* ctl;
     int* nfail_total;
     int pad_inactive;  // exact-only pipeline: the exact finalize also pads unrouted queries
+    const int* cpos;   // large-batch path: candidate row of query qi (compacted); NULL = qi
+    int lists_from_ctl;  // large-batch path: the number of lists is ctl->n_lists (decided on the device)
 };
 
 constexpr int RR_FIN_THREADS = 256;
@@ -326,9 +347,11 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     __shared__ uint32_t sel_r[RR_FIN_MAXSEL];
     extern __shared__ __align__(16) float q_sm[];  // [d_pad] (RESCORE only)
 
-    const float* cs = a.cand_s + (int64_t)qi * a.cand_stride;
-    const uint32_t* cr = a.cand_r + (int64_t)qi * a.cand_stride;
-    const int n_cand = a.n_lists * a.depth;
+    const int crow = (RESCORE && a.cpos) ? a.cpos[qi] : qi;
+    const float* cs = a.cand_s + (int64_t)crow * a.cand_stride;
+    const uint32_t* cr = a.cand_r + (int64_t)crow * a.cand_stride;
+    const int n_lists = (RESCORE && a.lists_from_ctl) ? a.ctl->n_lists : a.n_lists;
+    const int n_cand = n_lists * a.depth;
 
     if (tid == 0) {
         s_prefix = 0ull;
@@ -346,7 +369,7 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     // T = largest tail of a full list (every dropped row scores <= T); n_valid
     float T = RR_NEG_INF;
     int nv = 0;
-    for (int l = tid; l < a.n_lists; l += blockDim.x) {
+    for (int l = tid; l < n_lists; l += blockDim.x) {
         const int64_t o = (int64_t)l * a.depth + a.depth - 1;
         if (cr[o] != RR_NO_ROW) T = fmaxf(T, cs[o]);
     }
@@ -580,8 +603,8 @@ extern "C" int rr_index_create(int d, int64_t capacity_rows, int device, rr_inde
     h->sm_count = prop.multiProcessorCount;
     e = cudaMalloc(&h->max_norm_bits, 16);
     if (e == cudaSuccess) e = cudaMemset(h->max_norm_bits, 0, 16);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_nfail_total, 16);
-    if (e == cudaSuccess) e = cudaMemset(h->d_nfail_total, 0, 16);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_nfail_total, 32);
+    if (e == cudaSuccess) e = cudaMemset(h->d_nfail_total, 0, 32);
     if (e != cudaSuccess) {
         rr_set_error("rr_index_create: %s", cudaGetErrorString(e));
         rr_index_destroy(h);
@@ -757,16 +780,18 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
     rr_device_guard g(h->device);
     int rc = rr_flush_events(h);
     if (rc != RR_OK) return rc;
-    unsigned long long ctr[2] = {0, 0};  // [0] low int = certificate failures, [1] = bytes really scanned
-    RR_CUDA_CHECK(cudaMemcpy(ctr, h->d_nfail_total, 16, cudaMemcpyDeviceToHost));
+    unsigned long long ctr[4] = {0, 0, 0, 0};  // [0] low int = certificate failures, [1] bytes, [2] flops
+    RR_CUDA_CHECK(cudaMemcpy(ctr, h->d_nfail_total, 32, cudaMemcpyDeviceToHost));
     h->stats.exact_rescans = (int)(ctr[0] & 0xFFFFFFFFull);
     h->stats.scan_bytes_total = (int64_t)ctr[1];
+    h->stats.scan_flops_total = (int64_t)ctr[2];
     *out = h->stats;
     if (reset) {
         h->stats.scan_ms_total = 0;
         h->stats.scan_launches = 0;
         h->stats.scan_bytes_total = 0;
-        RR_CUDA_CHECK(cudaMemset(h->d_nfail_total + 2, 0, 8));
+        h->stats.scan_flops_total = 0;
+        RR_CUDA_CHECK(cudaMemset(h->d_nfail_total + 2, 0, 16));
     }
     return RR_OK;
 }
@@ -808,6 +833,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     const size_t o_act = carve((size_t)nq_pad);
     const size_t o_ff = carve((size_t)nq_pad);
     const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
+    const size_t o_cp = carve((size_t)nq_pad * sizeof(int));
     const size_t o_cs = carve((size_t)nq * cand_stride * sizeof(float));
     const size_t o_cr = carve((size_t)nq * cand_stride * sizeof(uint32_t));
     if (off > h->scratch_bytes) {
@@ -822,13 +848,19 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     uint8_t* active = (uint8_t*)(base + o_act);
     uint8_t* fail_flags = (uint8_t*)(base + o_ff);
     int* fail_list = (int*)(base + o_fl);
+    int* cpos = (int*)(base + o_cp);
     float* cand_s = (float*)(base + o_cs);
     uint32_t* cand_r = (uint32_t*)(base + o_cr);
 
     RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
+    if (use_gemm) {
+        rr_compact_queries_kernel<<<1, 1024, 0, stream>>>(mask_dev, mask_stride, nq, cpos, ctl);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
+    }
     rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, mask_dev, mask_stride,
                                                        qbf, qnorm, active, fail_flags, fail_list, ctl,
-                                                       (use_tc || use_gemm) ? 0 : 1);
+                                                       (use_tc || use_gemm) ? 0 : 1, use_gemm ? cpos : nullptr);
     RR_CUDA_CHECK(cudaGetLastError());
     rr_count_launch(1);
 
@@ -855,6 +887,8 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     fa.ctl = ctl;
     fa.nfail_total = h->d_nfail_total;
     fa.pad_inactive = (use_tc || use_gemm) ? 0 : 1;
+    fa.cpos = nullptr;
+    fa.lists_from_ctl = 0;
 
     if (use_gemm) {
         // one launch covers the whole chunk: queries stationary in TMEM, corpus read once
@@ -864,17 +898,17 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
                 if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
             RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
         }
-        int n_lists = 0;
-        int rc = rr_gemm_scan_launch(h, qbf, nq, active, &ctl->any_active, cand_s, cand_r, cand_stride, &n_lists,
-                                     prof ? reinterpret_cast<unsigned long long*>(h->d_nfail_total + 2) : nullptr,
-                                     stream);
+        int rc = rr_gemm_scan_launch(h, qbf, nq, ctl, cand_s, cand_r, cand_stride,
+                                     prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr, stream);
         if (rc != RR_OK) return rc;
         rr_count_launch(1);
         if (prof) {
             RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
             h->ev_used += 2;
         }
-        fa.n_lists = n_lists;
+        fa.n_lists = 0;
+        fa.lists_from_ctl = 1;
+        fa.cpos = cpos;
         fa.depth = RR_GEMM_LIST_DEPTH;
         rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
         RR_CUDA_CHECK(cudaGetLastError());
@@ -894,7 +928,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
             int rc = rr_tc_scan_launch(h, qbf, nq_pad, p0, nqt, active + p0, &ctl->any_active,
                                        cand_s + (size_t)p0 * cand_stride, cand_r + (size_t)p0 * cand_stride,
                                        cand_stride, &n_lists,
-                                       prof ? reinterpret_cast<unsigned long long*>(h->d_nfail_total + 2) : nullptr,
+                                       prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr,
                                        stream);
             if (rc != RR_OK) return rc;
             rr_count_launch(1);
@@ -1045,7 +1079,7 @@ extern "C" int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq,
     rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, nullptr, 0,
                                                        (uint16_t*)(base + o_qbf), (float*)(base + o_qn),
                                                        (uint8_t*)(base + o_act), (uint8_t*)(base + o_ff),
-                                                       (int*)(base + o_fl), ctl, 0);
+                                                       (int*)(base + o_fl), ctl, 0, nullptr);
     RR_CUDA_CHECK(cudaGetLastError());
     RR_CUDA_CHECK(cudaMemsetAsync(cand_s_dev, 0xFF, (size_t)nq * capacity * sizeof(float), stream));
     RR_CUDA_CHECK(cudaMemsetAsync(cand_r_dev, 0xFF, (size_t)nq * capacity * sizeof(uint32_t), stream));

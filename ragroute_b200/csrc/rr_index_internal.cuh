@@ -54,10 +54,24 @@ struct rr_index {
 
     // stats
     rr_index_stats stats = {};
-    int* d_nfail_total = nullptr;  // device: [0] certificate failures (int); bytes 8..15: scanned-bytes counter (u64)
+    int* d_nfail_total = nullptr;  // device counters (32 bytes): [0] certificate failures (int);
+                                   // bytes 8..15 scanned bytes (u64); bytes 16..23 scored flops (u64)
     static constexpr int kEvPool = 4096;  // 2048 timed launches between two rr_index_get_stats calls
     cudaEvent_t ev_pool[kEvPool] = {};
     int ev_used = 0;
+};
+
+// Control block of one query chunk (device memory, zeroed per chunk).
+struct rr_chunk_ctl {
+    int n_fail;      // queries needing the exact path
+    int any_active;  // at least one query is routed to this source
+    int n_active;    // large-batch path: routed queries (they are compacted to rows [0, n_active))
+    int n_lists;     // large-batch path: candidate lists per query the scan produced
+};
+// profiling counters handed to the scan kernels (or NULL): [0] bytes streamed, [1] flops scored
+struct rr_scan_counters {
+    unsigned long long bytes;
+    unsigned long long flops;
 };
 
 // rr_scan_tc.cu: launch the tcgen05 scan for one pass of <= qtile queries: rows
@@ -67,7 +81,7 @@ struct rr_index {
 // the pass's first query) and reports the number of lists per query.
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
-                      int64_t cand_stride, int* n_lists_out, unsigned long long* bytes_scanned_dev,
+                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev,
                       cudaStream_t stream);
 // number of candidate lists per query the tc scan produces for this index
 int rr_tc_scan_num_lists(const rr_index* h);
@@ -79,10 +93,12 @@ int rr_tc_scan_qtile(const rr_index* h);
 int rr_make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int d_pad, int box_rows);
 
 // rr_scan_gemm.cu: large-batch scan (queries stationary in TMEM).  qbf16 holds
-// ceil(nq / 128) * 128 zero-padded rows; active has as many entries.  Produces one list of
-// RR_GEMM_LIST_DEPTH entries per (corpus slice, query); *n_lists_out = number of slices.
+// ceil(nq / 128) * 128 rows: the ctl->n_active ROUTED queries compacted first, zero rows after
+// them.  The kernel sizes its query tiles / corpus slices from ctl->n_active on the device,
+// writes one list of RR_GEMM_LIST_DEPTH entries per (corpus slice, compact query) and stores
+// the number of slices in ctl->n_lists.
 bool rr_gemm_scan_supported(const rr_index* h);
 int rr_gemm_scan_max_lists(const rr_index* h);
-int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, const uint8_t* active_dev,
-                        const int* any_active_dev, float* cand_s, uint32_t* cand_r, int64_t cand_stride,
-                        int* n_lists_out, unsigned long long* bytes_scanned_dev, cudaStream_t stream);
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk_ctl* ctl_dev, float* cand_s,
+                        uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+                        cudaStream_t stream);

@@ -51,17 +51,14 @@ struct GemmParams {
     int n_tiles;     // ceil(n_rows / kNT)
     int num_kc;      // d_pad / 64
     int d_pad;
-    int nq;          // valid queries in the chunk
-    int nqt;         // query tiles of 128
-    int n_slices;    // corpus slices = gridDim.x / nqt
     int stages;
     int acc_stages;
     uint64_t l2_hint;
-    const uint16_t* qbf16;  // [nqt * 128][d_pad] bf16, zero padded
-    const uint8_t* active;  // [nqt * 128]
-    const int* any_active;
-    unsigned long long* bytes_scanned;
-    float* cand_s;  // [query][slice][kDepth]
+    uint64_t l2_hint_shared;  // when several query tiles share a corpus slice
+    const uint16_t* qbf16;    // [ceil(nq / 128) * 128][d_pad] bf16: routed queries first, then zero rows
+    rr_chunk_ctl* ctl;        // n_active (in), n_lists (out)
+    rr_scan_counters* counters;
+    float* cand_s;  // [compact query][slice][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
 };
@@ -106,9 +103,24 @@ static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA b
 
 __global__ void __launch_bounds__(kThreads, 1)
 rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
-    if (*p.any_active == 0) return;  // no query routed to this source: do not touch the corpus
-    if (p.bytes_scanned && blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(p.bytes_scanned, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
+    // Work split, decided on the device from the number of ROUTED queries: nqt query tiles of
+    // 128 (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
+    const int n_active = p.ctl->n_active;
+    if (n_active == 0) return;  // no query routed to this source: do not touch the corpus
+    const int nqt = (n_active + kQTile - 1) / kQTile;
+    const int n_slices = max(1, min((int)gridDim.x / nqt, p.n_tiles));
+    const int qt = blockIdx.x % nqt;
+    const int slice = blockIdx.x / nqt;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        p.ctl->n_lists = n_slices;
+        if (p.counters) {
+            atomicAdd(&p.counters->bytes, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
+            atomicAdd(&p.counters->flops,
+                      2ull * (unsigned long long)n_active * (unsigned long long)p.n_rows * (unsigned long long)p.d_pad);
+        }
+    }
+    if (slice >= n_slices) return;  // leftover CTAs (gridDim.x is not a multiple of nqt)
+    const uint64_t l2_hint = (nqt > 1) ? p.l2_hint_shared : p.l2_hint;
 
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -126,8 +138,6 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int qt = blockIdx.x % p.nqt;
-    const int slice = blockIdx.x / p.nqt;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
@@ -160,13 +170,13 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
-        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+        for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             for (int kc = 0; kc < p.num_kc; ++kc) {
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
                 if (elect_one_sync()) {
                     mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
                     tma_load_2d(x_base + stage * kStageBytes, &tmap_x, smem_u32(bar_full + stage),
-                                kc * RR_TC_KCHUNK, tile * kNT, p.l2_hint);
+                                kc * RR_TC_KCHUNK, tile * kNT, l2_hint);
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -183,7 +193,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
-        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+        for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
@@ -237,12 +247,11 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
             lr_w[i] = RR_NO_ROW;
         }
         __syncwarp();
-        const bool act = (qg < p.nq) && (p.active[qg] != 0);
-        float thr = act ? RR_NEG_INF : __builtin_huge_valf();
+        float thr = (qg < n_active) ? RR_NEG_INF : __builtin_huge_valf();
 
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = slice; tile < p.n_tiles; tile += p.n_slices) {
+        for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             mbar_wait(smem_u32(bar_acc_full + acc), acc_phase);
             tc_fence_after();
             const uint32_t t_acc = lane_addr + a_cols + (uint32_t)(acc * kNT);
@@ -301,7 +310,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
         // publish sorted: [query][list = slice][kDepth], lane e writes entry e
         for (int i = 0; i < 32; ++i) {
             const int qi = qt * kQTile + quad * 32 + i;
-            if (qi >= p.nq) break;
+            if (qi >= n_active) break;
             float es = ls_w[i * kDepth + lane];
             uint32_t er = lr_w[i * kDepth + lane];
             rr_warp_sort(es, er, lane);
@@ -328,9 +337,9 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
-int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, const uint8_t* active_dev,
-                        const int* any_active_dev, float* cand_s, uint32_t* cand_r, int64_t cand_stride,
-                        int* n_lists_out, unsigned long long* bytes_scanned_dev, cudaStream_t stream) {
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk_ctl* ctl_dev, float* cand_s,
+                        uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+                        cudaStream_t stream) {
     RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
     RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
     if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
@@ -344,31 +353,28 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, const ui
     p.n_tiles = (int)((h->n + kNT - 1) / kNT);
     p.num_kc = h->d_pad / RR_TC_KCHUNK;
     p.d_pad = h->d_pad;
-    p.nq = nq;
-    p.nqt = (nq + kQTile - 1) / kQTile;
-    p.n_slices = std::max(1, std::min(h->sm_count / p.nqt, p.n_tiles));
     p.acc_stages = std::min(kMaxAcc, ((int)kTmemCols - h->d_pad / 2) / kNT);
     const size_t fixed = 1024 + (size_t)kDepth * kQTile * 8 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
     p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / kStageBytes);
     const size_t smem = fixed + (size_t)p.stages * kStageBytes;
     // sibling CTAs (other query tiles, same slice) re-read each tile from L2 right away
-    p.l2_hint = (p.nqt > 1) ? kTmaEvictNormal : kTmaEvictFirst;
+    p.l2_hint = kTmaEvictFirst;
+    p.l2_hint_shared = kTmaEvictNormal;
     p.qbf16 = qbf16_dev;
-    p.active = active_dev;
-    p.any_active = any_active_dev;
-    p.bytes_scanned = bytes_scanned_dev;
+    p.ctl = ctl_dev;
+    p.counters = counters_dev;
     p.cand_s = cand_s;
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
-    RR_REQUIRE((int64_t)p.n_slices * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
+    RR_REQUIRE((int64_t)h->sm_count * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
         attr_done[h->device & 63] = true;
     }
-    *n_lists_out = p.n_slices;
-    rr_gemm_scan_kernel<<<p.n_slices * p.nqt, kThreads, smem, stream>>>(h->tmap_hi, p);
+    // every SM gets a CTA; the kernel itself splits them into query tiles x corpus slices
+    rr_gemm_scan_kernel<<<h->sm_count, kThreads, smem, stream>>>(h->tmap_hi, p);
     RR_CUDA_CHECK(cudaGetLastError());
     return RR_OK;
 }

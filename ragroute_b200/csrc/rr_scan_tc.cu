@@ -45,7 +45,7 @@ struct TcParams {
     int stages;
     const uint8_t* active;   // [nq_tile]
     const int* any_active;   // device flag: 0 -> nothing routed here, exit at once
-    unsigned long long* bytes_scanned;  // profiling: algorithmic bytes of passes that really ran (or NULL)
+    rr_scan_counters* counters;  // profiling: bytes streamed / flops scored by passes that really ran (or NULL)
     float* cand_s;           // [query][list][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
@@ -93,8 +93,13 @@ __global__ void __launch_bounds__(kThreads, 1)
 rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                   const TcParams p) {
     if (*p.any_active == 0) return;  // no query routed to this source: do not touch the corpus
-    if (p.bytes_scanned && blockIdx.x == 0 && threadIdx.x == 0)
-        atomicAdd(p.bytes_scanned, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
+    if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) {
+        int n_act = 0;
+        for (int q = 0; q < p.nq_tile; ++q) n_act += p.active[q] ? 1 : 0;
+        atomicAdd(&p.counters->bytes, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
+        atomicAdd(&p.counters->flops,
+                  2ull * (unsigned long long)n_act * (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 64ull);
+    }
 
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     // carve (all offsets multiples of 1024 for the swizzled tiles)
@@ -328,7 +333,7 @@ int rr_tc_scan_num_lists(const rr_index* h) { return h->sm_count * RR_TC_EPI_WAR
 
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
-                      int64_t cand_stride, int* n_lists_out, unsigned long long* bytes_scanned_dev,
+                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev,
                       cudaStream_t stream) {
     const int qt = rr_tc_scan_qtile(h);
     RR_REQUIRE(qt > 0 && nq_tile >= 1 && nq_tile <= qt, "rr_tc_scan_launch: bad query tile");
@@ -353,7 +358,7 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
     p.stages = pl.stages;
     p.active = active_dev;
     p.any_active = any_active_dev;
-    p.bytes_scanned = bytes_scanned_dev;
+    p.counters = counters_dev;
     p.cand_s = cand_s;
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
