@@ -114,6 +114,12 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------- CPU reference arm
+def cpu_sample_rows(rows_at_64: int, batch: int) -> int:
+    """Row sample of the CPU arm: sized for batch 64 and shrunk for larger batches so that one
+    step stays a bounded amount of CPU work (rows x queries constant)."""
+    return max(4096, int(rows_at_64 * 64 / max(batch, 64)))
+
+
 def cpu_sample_plan(rows: dict, sample_rows_total: int):
     total = sum(rows.values())
     plan = {}
@@ -199,7 +205,8 @@ def reference_main(args, rows, workload):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    qps, ms_sample, info = run_cpu_reference(rows, args.batch, args.steps, args.warmup, args.cpu_sample_rows)
+    qps, ms_sample, info = run_cpu_reference(rows, args.batch, args.steps, args.warmup,
+                                             cpu_sample_rows(args.cpu_sample_rows, args.batch))
     sample = (f"{sum(info['rows_sampled'].values())} of {sum(rows.values())} rows ({info['row_fraction']:.4%}, "
               f"proportional per source), batch {args.batch}, FAISS-restated sequential scan of routed pairs only "
               f"(mask density {info['mask_density']:.2f}), OpenMP over queries on {info['cores']} threads; "
@@ -319,10 +326,12 @@ def gpu_main(args, rows, workload):
         st = [ix.stats(reset=True) for ix in fed.indexes]
         scan_ms = sum(s["scan_ms_total"] for s in st)
         scan_bytes = sum(s["scan_bytes_total"] for s in st)
+        scan_flops = sum(s["scan_flops_total"] for s in st)
         scan_n = sum(s["scan_launches"] for s in st)
         rescans = sum(s["exact_rescans"] for s in st)
         return {"ms_total": ms_total, "per_step": per_step, "launches": int(sum_over_ranks(l1 - l0)),
-                "scan_ms": scan_ms, "scan_bytes": scan_bytes, "scan_launches": scan_n, "exact_rescans": rescans}
+                "scan_ms": scan_ms, "scan_bytes": scan_bytes, "scan_flops": scan_flops, "scan_launches": scan_n,
+                "exact_rescans": rescans}
 
     peaks = {}
     try:
@@ -331,7 +340,42 @@ def gpu_main(args, rows, workload):
     except Exception:  # noqa: BLE001
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured copy)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    # the scan runs inside a long step under the power cap: the sustained cuBLAS figure is the denominator
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    tc_src = ("MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, seconds-long loop)" if "bf16_tflops_sustained" in peaks
+              else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)")
+    try:
+        with open(os.path.join(REPO, "profiles", "scan_traffic.json")) as f:
+            traffic_db = json.load(f)
+    except Exception:  # noqa: BLE001
+        traffic_db = {}
+
+    def roofline_of(run: dict, batch: int) -> dict:
+        """Roofline entry of the dominant kernel of a run (rank 0's launches, CUDA events on the
+        launching stream).  batch <= 64: the swap-AB scan, HBM-bound (intensity = batch flop/byte);
+        larger batches: the queries-in-TMEM scan, bound by the bf16 tensor pipe."""
+        n = run["scan_launches"]
+        if not n:
+            return {"bound": None, "achieved": None, "peak": None, "frac": None, "traffic": None}
+        small = batch <= 64
+        key = "rr_tc_scan_kernel" if small else "rr_gemm_scan_kernel"
+        tj = traffic_db.get(key, {})
+        traffic = tj.get("dram_over_algorithmic", 0) * run["scan_bytes"] / n if tj else None
+        common = {"kernel": key, "launches_timed": n, "avg_launch_ms": run["scan_ms"] / n,
+                  "kernel_share_of_step": run["scan_ms"] / max(run["ms_total"], 1e-9),
+                  "algorithmic_bytes_per_launch": run["scan_bytes"] / n,
+                  "algorithmic_flops_per_launch": run["scan_flops"] / n,
+                  "traffic": traffic,
+                  "traffic_source": ("ncu dram read+write / algorithmic bytes = %.5f (%s), scaled to this launch size"
+                                     % (tj["dram_over_algorithmic"], tj["source"])) if tj else None}
+        gbs = run["scan_bytes"] / max(run["scan_ms"], 1e-9) * 1e-6
+        tfs = run["scan_flops"] / max(run["scan_ms"], 1e-9) * 1e-9
+        if small:
+            return {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                    "peak_source": hbm_src, "tflops": tfs, **common}
+        return {"bound": "tensor", "achieved": tfs, "peak": tc_peak, "unit": "TFLOP/s", "frac": tfs / tc_peak,
+                "peak_source": tc_src, "hbm_gbs": gbs, **common}
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     B = args.batch
@@ -339,40 +383,31 @@ def gpu_main(args, rows, workload):
     e2e_run = measure(B, args.steps, args.warmup, host=True)
     qps = B * args.steps / (dev_run["ms_total"] * 1e-3)
     qps_e2e = B * args.steps / (e2e_run["ms_total"] * 1e-3)
-    # rank 0's scan kernels: algorithmic bytes (rows * d_pad * 2, the bf16 plane once per pass) / event time
-    achieved = dev_run["scan_bytes"] / max(dev_run["scan_ms"], 1e-9) * 1e-6 if dev_run["scan_launches"] else None
-    # DRAM traffic per launch: the ncu --set full capture (profiles/scan_traffic.json) measured
-    # dram bytes / algorithmic bytes for this kernel; scale it to this run's launch size.
-    traffic, traffic_src = None, None
-    try:
-        with open(os.path.join(REPO, "profiles", "scan_traffic.json")) as f:
-            tj = json.load(f)
-        if dev_run["scan_launches"]:
-            traffic = tj["dram_over_algorithmic"] * dev_run["scan_bytes"] / dev_run["scan_launches"]
-            traffic_src = ("ncu dram read+write / algorithmic bytes = %.5f (%s), scaled to this launch size"
-                           % (tj["dram_over_algorithmic"], tj["source"]))
-    except Exception:  # noqa: BLE001
-        pass
 
     sweep = []
+    roofline_small = None
     if args.sweep:
         for b in [int(x) for x in args.sweep.split(",") if x]:
             if b == B:
                 r = dev_run
                 st_ = args.steps
             else:
-                st_ = max(3, min(args.steps, int(args.sweep_ms_budget / max(1.0, dev_run["ms_total"] / args.steps
-                                                                             * max(1, b // 64)))))
+                per_step = dev_run["ms_total"] / args.steps * max(b, 64) / max(B, 64)
+                st_ = max(3, min(30, int(args.sweep_ms_budget / max(1.0, per_step))))
                 r = measure(b, st_, 3, host=False)
+            rf = roofline_of(r, b)
             sweep.append({"batch": b, "steps": st_, "qps": b * st_ / (r["ms_total"] * 1e-3),
                           "p50_ms": pct(r["per_step"], 50), "p99_ms": pct(r["per_step"], 99),
-                          "scan_gbs": (r["scan_bytes"] / max(r["scan_ms"], 1e-9) * 1e-6) if r["scan_launches"] else None,
+                          "bound": rf["bound"], "achieved": rf["achieved"], "unit": rf.get("unit"), "frac": rf["frac"],
                           "exact_rescans": r["exact_rescans"]})
+            if b == 64:
+                roofline_small = rf
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.time()
-        cqps, cms, info = run_cpu_reference(rows, B, steps=2, warmup=1, sample_rows_total=args.cpu_sample_rows)
+        cqps, cms, info = run_cpu_reference(rows, B, steps=2, warmup=1,
+                                            sample_rows_total=cpu_sample_rows(args.cpu_sample_rows, B))
         cpu_baseline = {
             "value": cqps, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
             "sample": (f"{sum(info['rows_sampled'].values())} of {sum(rows.values())} rows "
@@ -402,13 +437,8 @@ def gpu_main(args, rows, workload):
                     "d2h_bytes_per_step": B * K * (4 + 8 + 8), "ms_per_step": e2e_run["ms_total"] / args.steps,
                     "p50_ms": pct(e2e_run["per_step"], 50), "p99_ms": pct(e2e_run["per_step"], 99)},
             "gpu_launches": dev_run["launches"],
-            "roofline": {"bound": "hbm", "kernel": "rr_tc_scan_kernel", "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
-                         "traffic_source": traffic_src,
-                         "peak_source": peak_src, "launches_timed": dev_run["scan_launches"],
-                         "kernel_share_of_step": dev_run["scan_ms"] / max(dev_run["ms_total"], 1e-9),
-                         "algorithmic_bytes_per_launch": (dev_run["scan_bytes"] / dev_run["scan_launches"])
-                         if dev_run["scan_launches"] else None},
+            "roofline": roofline_of(dev_run, B),
+            "roofline_small_batch": roofline_small,
             "exact_rescans": dev_run["exact_rescans"],
             "clocks": sampler.summary() if sampler else None,
             "cpu_baseline": cpu_baseline,
@@ -425,14 +455,15 @@ def gpu_main(args, rows, workload):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--batch", type=int, default=1024,
+                    help="queries per step; <= 64 is the HBM-bound regime, >= 128 the tensor-bound one")
     ap.add_argument("--routing", default="ragroute", choices=["ragroute", "all"])
     ap.add_argument("--rows-scale", type=float, default=1.0, help="scale every source's row count (debug)")
-    ap.add_argument("--sweep", default="", help="comma separated extra batch sizes, e.g. 1,8,64,256,1024")
+    ap.add_argument("--sweep", default="1,8,64,256", help="comma separated extra batch sizes ('' = none)")
     ap.add_argument("--sweep-ms-budget", type=float, default=1500.0)
     ap.add_argument("--cpu-sample-rows", type=int, default=600_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
