@@ -46,8 +46,17 @@ BYTES_PER_ELEM_STORED = 4  # two 16-bit planes
 D, K = 768, 32
 
 
+_REAL_STDOUT = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line: dict) -> None:
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 # --------------------------------------------------------------------------- clocks
@@ -221,7 +230,7 @@ def reference_main(args, rows, workload):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -445,7 +454,7 @@ def gpu_main(args, rows, workload):
         }
         if sweep:
             line["sweep"] = sweep
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -453,6 +462,12 @@ def gpu_main(args, rows, workload):
 
 
 def main():
+    # Rank 0 must print exactly ONE line on stdout: libraries (NCCL prints its version banner there)
+    # are sent to stderr; the JSON line goes to the saved descriptor.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
     ap.add_argument("--steps", type=int, default=20)
