@@ -8,15 +8,18 @@
 // approaches / exceeds the ridge (~215), so the corpus must be read from HBM once per
 // chunk of up to 1024 queries and every byte brought into an SM must be used against as
 // many queries as possible:
-//   * a tile of 128 queries lives in TENSOR MEMORY for the whole kernel as the UMMA A
-//     operand (TS form of tcgen05.mma: row m of A in TMEM lane m, 2 bf16 per 32-bit
-//     column; 768 dims = 384 columns), written once by tcgen05.st;
+//   * a tile of 128 queries is stationary for the whole kernel as the UMMA A operand: its
+//     first 512 dimensions live in TENSOR MEMORY (TS form of tcgen05.mma: row m of A in
+//     TMEM lane m, 2 bf16 per 32-bit column = 256 columns, written once by tcgen05.st),
+//     the remaining <= 256 dimensions in shared memory (SS form, 64 KB, loaded once by TMA).
+//     The split leaves 256 TMEM columns = TWO accumulator stages, so the epilogue of tile i
+//     runs under the MMAs of tile i+1 (with all 768 dims in TMEM only one stage fits and the
+//     tensor pipe idles ~25 % of the time waiting for the accumulator to drain);
 //   * corpus rows stream through shared memory as the B operand, 128 rows x 64 k per
 //     16 KB TMA stage (128B swizzle), ring of 12 stages (192 KB in flight per SM); UMMA
 //     N = 128 because one tcgen05.mma costs >= 45 cycles whatever its N (measured:
 //     scripts/microbench/umma_rate.cu), so N = 64 would waste 30 % of the tensor pipe;
-//   * the remaining TMEM columns hold 1-3 accumulator stages of 128 fp32 columns
-//     (128 queries x 128 corpus rows each);
+//   * two accumulator stages of 128 fp32 columns (128 queries x 128 corpus rows each);
 //   * epilogue orientation: TMEM lane = query, so every epilogue THREAD owns one query:
 //     its running threshold sits in a register and the 128 scores of a tile cost one max
 //     tree + one compare.  Survivors are inserted WARP-COOPERATIVELY into that query's
@@ -37,12 +40,15 @@ namespace {
 using namespace rr_ptx;
 
 constexpr int kNT = RR_GEMM_TILE_ROWS;               // corpus rows per MMA (UMMA N)
-constexpr int kStageBytes = kNT * RR_TC_KCHUNK * 2;  // 16 KB
+constexpr int kChunkBytes = kNT * RR_TC_KCHUNK * 2;  // one TMA box: 128 rows x 64 k = 16 KB
+constexpr int kStageKc = 2;                          // K-chunks per pipeline stage: one barrier wait per 8 MMAs
+constexpr int kStageBytes = kStageKc * kChunkBytes;  // 32 KB
 constexpr int kDepth = RR_GEMM_LIST_DEPTH;
 constexpr int kQTile = RR_GEMM_QTILE;  // 128 queries = TMEM lanes
 constexpr int kThreads = 192;
-constexpr int kMaxStages = 12;
-constexpr int kMaxAcc = 3;
+constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 2;
+constexpr int kMaxATmemKc = ((int)512 - kMaxAcc * RR_GEMM_TILE_ROWS) / 32;  // 8 K-chunks = 512 dims of A in TMEM
 constexpr int kSmemLimit = 227 * 1024;
 constexpr uint32_t kTmemCols = 512;
 
@@ -53,6 +59,8 @@ struct GemmParams {
     int d_pad;
     int stages;
     int acc_stages;
+    int a_tmem_kc;   // leading K-chunks of the query tile held in TMEM
+    int a_smem_kc;   // trailing K-chunks held in shared memory
     uint64_t l2_hint;
     uint64_t l2_hint_shared;  // when several query tiles share a corpus slice
     const uint16_t* qbf16;    // [ceil(nq / 128) * 128][d_pad] bf16: routed queries first, then zero rows
@@ -102,7 +110,8 @@ __device__ __noinline__ float epi_take(unsigned b, float v, uint32_t row, float 
 static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA box of the hi plane");
 
 __global__ void __launch_bounds__(kThreads, 1)
-rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams p) {
+rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
+                    const GemmParams p) {
     // Work split, decided on the device from the number of ROUTED queries: nqt query tiles of
     // 128 (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
     const int n_active = p.ctl->n_active;
@@ -126,15 +135,17 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                ~(uintptr_t)1023);
     uint8_t* x_sm = base;
-    float* ls = reinterpret_cast<float*>(x_sm + p.stages * kStageBytes);  // [128 queries][kDepth]
+    uint8_t* a_sm = x_sm + p.stages * kStageBytes;  // [a_smem_kc][128 queries x 64 k], 128B swizzle
+    float* ls = reinterpret_cast<float*>(a_sm + p.a_smem_kc * kChunkBytes);  // [128 queries][kDepth]
     uint32_t* lr = reinterpret_cast<uint32_t*>(ls + kDepth * kQTile);
     uint64_t* bars = reinterpret_cast<uint64_t*>(lr + kDepth * kQTile);
     uint64_t* bar_full = bars;
     uint64_t* bar_empty = bars + kMaxStages;
     uint64_t* bar_acc_full = bars + 2 * kMaxStages;
     uint64_t* bar_acc_empty = bar_acc_full + kMaxAcc;
-    uint64_t* bar_a = bar_acc_empty + kMaxAcc;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_a + 1);
+    uint64_t* bar_a = bar_acc_empty + kMaxAcc;   // query tile written to TMEM (4 epilogue warps)
+    uint64_t* bar_aq = bar_a + 1;                // query tile tail landed in shared memory (TMA)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_aq + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -150,6 +161,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
             mbar_init(smem_u32(bar_acc_empty + i), 4);
         }
         mbar_init(smem_u32(bar_a), 4);
+        mbar_init(smem_u32(bar_aq), 1);
         fence_barrier_init();
     } else if (warp == 1) {
         tmem_alloc(smem_u32(tmem_slot), kTmemCols);
@@ -158,7 +170,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t a_cols = (uint32_t)p.num_kc * 32u;  // d_pad / 2
+    const uint32_t a_cols = (uint32_t)p.a_tmem_kc * 32u;  // TMEM columns of the query tile
     const uint32_t acc_base = tmem_base + a_cols;
 
     // Warps 0 and 1 run their loops converged (all 32 lanes wait on the barriers) and elect one
@@ -170,13 +182,22 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
+        if (p.a_smem_kc > 0 && elect_one_sync()) {
+            mbar_arrive_expect_tx(smem_u32(bar_aq), (uint32_t)(p.a_smem_kc * kChunkBytes));
+            for (int c = 0; c < p.a_smem_kc; ++c)
+                tma_load_2d(smem_u32(a_sm + c * kChunkBytes), &tmap_q, smem_u32(bar_aq),
+                            (p.a_tmem_kc + c) * RR_TC_KCHUNK, qt * kQTile, kTmaEvictLast);
+        }
+        __syncwarp();
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
-            for (int kc = 0; kc < p.num_kc; ++kc) {
+            for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
+                const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(smem_u32(bar_full + stage), kStageBytes);
-                    tma_load_2d(x_base + stage * kStageBytes, &tmap_x, smem_u32(bar_full + stage),
-                                kc * RR_TC_KCHUNK, tile * kNT, l2_hint);
+                    mbar_arrive_expect_tx(smem_u32(bar_full + stage), (uint32_t)(nk * kChunkBytes));
+                    for (int c = 0; c < nk; ++c)
+                        tma_load_2d(x_base + stage * kStageBytes + c * kChunkBytes, &tmap_x,
+                                    smem_u32(bar_full + stage), (kc + c) * RR_TC_KCHUNK, tile * kNT, l2_hint);
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -188,27 +209,55 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
     } else if (warp == 1) {
         // ===================== MMA issuer =======================
         constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kNT);
-        mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM
+        mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM ...
+        if (p.a_smem_kc > 0) mbar_wait(smem_u32(bar_aq), 0);  // ... and its tail in shared memory
         tc_fence_after();
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
+        const uint32_t a_base = smem_u32(a_sm);
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
             tc_fence_after();
             const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
-            for (int kc = 0; kc < p.num_kc; ++kc) {
+            for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
+                const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
                 const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageBytes) >> 4) & 0x3FFFu);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(kc * 32);
+                const uint64_t a_desc =
+                    kUmmaDescSw128Hi | (uint64_t)(((a_base + (kc - p.a_tmem_kc) * kChunkBytes) >> 4) & 0x3FFFu);
                 if (elect_one_sync()) {
-                    umma_bf16_ts(d_tmem, a_tmem, b_desc, idesc, (uint32_t)(kc != 0));
-                    umma_bf16_ts(d_tmem, a_tmem + 8, b_desc + 2, idesc, 1u);
-                    umma_bf16_ts(d_tmem, a_tmem + 16, b_desc + 4, idesc, 1u);
-                    umma_bf16_ts(d_tmem, a_tmem + 24, b_desc + 6, idesc, 1u);
+                    // a_tmem_kc is even whenever part of the tile lives in shared memory, so a stage is
+                    // all-TMEM or all-smem
+                    if (kc < p.a_tmem_kc) {  // A from tensor memory
+#pragma unroll
+                        for (int c = 0; c < kStageKc; ++c) {
+                            if (c < nk) {
+                                const uint32_t at = a_tmem + c * 32;
+                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkBytes >> 4));
+                                umma_bf16_ts(d_tmem, at, bd, idesc, (uint32_t)((kc | c) != 0));
+                                umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1u);
+                                umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1u);
+                                umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1u);
+                            }
+                        }
+                    } else {  // A from shared memory
+#pragma unroll
+                        for (int c = 0; c < kStageKc; ++c) {
+                            if (c < nk) {
+                                const uint64_t ad = a_desc + (uint64_t)(c * (kChunkBytes >> 4));
+                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkBytes >> 4));
+                                umma_bf16(d_tmem, ad, bd, idesc, 1u);
+                                umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                            }
+                        }
+                    }
                     umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
-                    if (kc == p.num_kc - 1) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
+                    if (kc + kStageKc >= p.num_kc) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -331,8 +380,8 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const GemmParams
 }  // namespace
 
 bool rr_gemm_scan_supported(const rr_index* h) {
-    // the query tile (d_pad / 2 TMEM columns) must leave room for one 128-column accumulator
-    return h->d_pad / 2 + kNT <= (int)kTmemCols;
+    // 512 dims of the query tile in TMEM + at most 256 more in shared memory
+    return h->d_pad <= (kMaxATmemKc + 4) * RR_TC_KCHUNK;
 }
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
@@ -353,8 +402,11 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk
     p.n_tiles = (int)((h->n + kNT - 1) / kNT);
     p.num_kc = h->d_pad / RR_TC_KCHUNK;
     p.d_pad = h->d_pad;
-    p.acc_stages = std::min(kMaxAcc, ((int)kTmemCols - h->d_pad / 2) / kNT);
-    const size_t fixed = 1024 + (size_t)kDepth * kQTile * 8 + (2 * kMaxStages + 2 * kMaxAcc + 1) * 8 + 16;
+    p.acc_stages = kMaxAcc;
+    p.a_tmem_kc = std::min(p.num_kc, kMaxATmemKc);
+    p.a_smem_kc = p.num_kc - p.a_tmem_kc;
+    const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)kDepth * kQTile * 8 +
+                         (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
     p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / kStageBytes);
     const size_t smem = fixed + (size_t)p.stages * kStageBytes;
     // sibling CTAs (other query tiles, same slice) re-read each tile from L2 right away
@@ -373,8 +425,13 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk
                                            kSmemLimit));
         attr_done[h->device & 63] = true;
     }
+    // the tail of each query tile is fetched by TMA from the bf16 query buffer
+    const int nq_rows = (nq + kQTile - 1) / kQTile * kQTile;
+    alignas(64) CUtensorMap tq;
+    int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, nq_rows, h->d_pad, kQTile);
+    if (rc != RR_OK) return rc;
     // every SM gets a CTA; the kernel itself splits them into query tiles x corpus slices
-    rr_gemm_scan_kernel<<<h->sm_count, kThreads, smem, stream>>>(h->tmap_hi, p);
+    rr_gemm_scan_kernel<<<h->sm_count, kThreads, smem, stream>>>(h->tmap_hi, tq, p);
     RR_CUDA_CHECK(cudaGetLastError());
     return RR_OK;
 }
