@@ -663,6 +663,7 @@ extern "C" int rr_index_reserve(rr_index_t* h, int64_t capacity_rows) {
     h->lo = nlo;
     h->cap = capacity_rows;
     h->tmap_hi_ptr = nullptr;
+    h->tmap_hi64_ptr = nullptr;
     return RR_OK;
 }
 
@@ -753,8 +754,8 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
     } else if (!strcmp(name, "profile")) {
         h->profile = value != 0;
     } else if (!strcmp(name, "scan_path")) {
-        RR_REQUIRE(value == RR_PATH_AUTO || value == RR_PATH_SMALL || value == RR_PATH_GEMM,
-                   "scan_path must be 0 (auto), 1 (64-query passes) or 2 (large-batch kernel)");
+        RR_REQUIRE(value == RR_PATH_AUTO || value == RR_PATH_SMALL || value == RR_PATH_GEMM || value == RR_PATH_GEMM_PAIR,
+                   "scan_path must be 0 (auto), 1 (64-query passes), 2 (large-batch kernel) or 3 (large-batch, CTA pairs)");
         h->scan_path = (int)value;
     } else {
         rr_set_error("rr_index_set_param: unknown parameter '%s'", name);
@@ -801,8 +802,14 @@ static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // Large-batch path: more than one 64-query pass and a dimension whose query tile fits TMEM.
 static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
     if (!rr_gemm_scan_supported(h) || h->scan_path == RR_PATH_SMALL) return false;
-    if (h->scan_path == RR_PATH_GEMM) return true;
+    if (h->scan_path == RR_PATH_GEMM || h->scan_path == RR_PATH_GEMM_PAIR) return true;
     return nq > RR_TC_MAX_QTILE;
+}
+// CTA pairs (256 queries per work unit) pay off once a chunk has more than one 128-query tile
+static int rr_gemm_cta_group(const rr_index* h, int nq) {
+    if (h->scan_path == RR_PATH_GEMM) return 1;
+    if (h->scan_path == RR_PATH_GEMM_PAIR) return 2;
+    return nq > RR_GEMM_QTILE ? 2 : 1;
 }
 
 // one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch path) queries
@@ -812,7 +819,8 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     const int qt = rr_tc_scan_qtile(h);  // 0: tc path unavailable for this d
     const bool use_gemm = (h->mode == RR_MODE_AUTO) && h->n > 0 && rr_use_gemm_path(h, nq);
     const bool use_tc = (h->mode == RR_MODE_AUTO) && qt > 0 && h->n > 0 && !use_gemm;
-    const int nq_pad = (int)rr_align_up((size_t)nq, use_gemm ? RR_GEMM_QTILE : RR_TC_MAX_QTILE);
+    const int gemm_cg = use_gemm ? rr_gemm_cta_group(h, nq) : 1;
+    const int nq_pad = (int)rr_align_up((size_t)nq, use_gemm ? RR_GEMM_QTILE * gemm_cg : RR_TC_MAX_QTILE);
     const int g_exact = h->sm_count * 2;
     const int64_t cand_stride =
         use_gemm ? std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
@@ -898,7 +906,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
                 if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
             RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
         }
-        int rc = rr_gemm_scan_launch(h, qbf, nq, ctl, cand_s, cand_r, cand_stride,
+        int rc = rr_gemm_scan_launch(h, qbf, nq, gemm_cg, ctl, cand_s, cand_r, cand_stride,
                                      prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr, stream);
         if (rc != RR_OK) return rc;
         rr_count_launch(1);

@@ -20,7 +20,7 @@ constexpr int RR_GEMM_TILE_ROWS = 128; // corpus rows per MMA in the large-batch
 constexpr int RR_GEMM_QTILE = 128;     // queries per CTA in the large-batch kernel (UMMA M, TMEM lanes)
 constexpr int RR_GEMM_LIST_DEPTH = 32; // entries per (CTA, query) list of the large-batch kernel
 constexpr int RR_GEMM_QCHUNK = 1024;   // queries per chunk on the large-batch path
-constexpr int RR_PATH_AUTO = 0, RR_PATH_SMALL = 1, RR_PATH_GEMM = 2;  // set_param "scan_path"
+constexpr int RR_PATH_AUTO = 0, RR_PATH_SMALL = 1, RR_PATH_GEMM = 2, RR_PATH_GEMM_PAIR = 3;  // set_param "scan_path"
 constexpr int RR_EXACT_MAX_QSUB = 16;  // queries per exact-scan launch
 
 struct rr_index {
@@ -51,6 +51,9 @@ struct rr_index {
     alignas(64) CUtensorMap tmap_hi;
     const void* tmap_hi_ptr = nullptr;
     int64_t tmap_hi_rows = -1;
+    alignas(64) CUtensorMap tmap_hi64;  // same plane, 64-row boxes (CTA pairs of the large-batch kernel)
+    const void* tmap_hi64_ptr = nullptr;
+    int64_t tmap_hi64_rows = -1;
 
     // stats
     rr_index_stats stats = {};
@@ -99,6 +102,8 @@ int rr_make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int 
 // the number of slices in ctl->n_lists.
 bool rr_gemm_scan_supported(const rr_index* h);
 int rr_gemm_scan_max_lists(const rr_index* h);
-int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk_ctl* ctl_dev, float* cand_s,
-                        uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+// cta_group: 1 = one CTA per 128-query tile; 2 = CTA pairs (cluster of 2, 256 queries per pair),
+// for which qbf16 holds ceil(nq / 256) * 256 rows.
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
+                        float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
                         cudaStream_t stream);

@@ -109,17 +109,26 @@ __device__ __noinline__ float epi_take(unsigned b, float v, uint32_t row, float 
 }
 static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA box of the hi plane");
 
+// CG = 1: one CTA per work unit (128 queries x 128-row corpus tiles).
+// CG = 2: a CTA PAIR per work unit (cluster of 2, tcgen05 cta_group::2): 256 queries (128 per
+//         CTA, each in its own TMEM) against the same 128-row corpus tiles, of which each CTA
+//         streams only 64 rows -- per SM half the L2->smem traffic and half the shared-memory
+//         operand reads per flop, which is what bounds CG = 1.
+template <int CG>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                     const GemmParams p) {
     // Work split, decided on the device from the number of ROUTED queries: nqt query tiles of
-    // 128 (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
+    // 128 * CG (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
     const int n_active = p.ctl->n_active;
     if (n_active == 0) return;  // no query routed to this source: do not touch the corpus
-    const int nqt = (n_active + kQTile - 1) / kQTile;
-    const int n_slices = max(1, min((int)gridDim.x / nqt, p.n_tiles));
-    const int qt = blockIdx.x % nqt;
-    const int slice = blockIdx.x / nqt;
+    const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
+    const int unit = (int)blockIdx.x / CG;                       // work unit = CTA or CTA pair
+    const int n_units = (int)gridDim.x / CG;
+    const int nqt = (n_active + kQTile * CG - 1) / (kQTile * CG);
+    const int n_slices = max(1, min(n_units / nqt, p.n_tiles));
+    const int qt = (unit % nqt) * CG + (int)rank;  // this CTA's 128-query tile
+    const int slice = unit / nqt;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         p.ctl->n_lists = n_slices;
         if (p.counters) {
@@ -130,12 +139,16 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
     if (slice >= n_slices) return;  // leftover CTAs (gridDim.x is not a multiple of nqt)
     const uint64_t l2_hint = (nqt > 1) ? p.l2_hint_shared : p.l2_hint;
+    // corpus rows / bytes of THIS CTA per tile chunk: all 128 rows (16 KB) or, in a pair, its 64 (8 KB)
+    constexpr int kRowsCta = kNT / CG;
+    constexpr int kChunkB = kChunkBytes / CG;
+    constexpr int kStageB = kStageKc * kChunkB;
 
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
                                                ~(uintptr_t)1023);
     uint8_t* x_sm = base;
-    uint8_t* a_sm = x_sm + p.stages * kStageBytes;  // [a_smem_kc][128 queries x 64 k], 128B swizzle
+    uint8_t* a_sm = x_sm + p.stages * kStageB;  // [a_smem_kc][128 queries x 64 k], 128B swizzle
     float* ls = reinterpret_cast<float*>(a_sm + p.a_smem_kc * kChunkBytes);  // [128 queries][kDepth]
     uint32_t* lr = reinterpret_cast<uint32_t*>(ls + kDepth * kQTile);
     uint64_t* bars = reinterpret_cast<uint64_t*>(lr + kDepth * kQTile);
@@ -150,6 +163,10 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
+    // Barrier protocol for a pair (CG = 2): the LEADER owns bar_full (armed by its producer with the
+    // bytes of both CTAs; both producers' TMA complete on it), bar_acc_empty and bar_a (both CTAs'
+    // epilogue warps arrive on them remotely); bar_empty and bar_acc_full exist in both CTAs and
+    // are signalled in both at once by the leader's multicast tcgen05.commit.
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_x);
         for (int i = 0; i < p.stages; ++i) {
@@ -158,16 +175,18 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
         for (int i = 0; i < p.acc_stages; ++i) {
             mbar_init(smem_u32(bar_acc_full + i), 1);
-            mbar_init(smem_u32(bar_acc_empty + i), 4);
+            mbar_init(smem_u32(bar_acc_empty + i), 4 * CG);
         }
-        mbar_init(smem_u32(bar_a), 4);
+        mbar_init(smem_u32(bar_a), (4 + (p.a_smem_kc > 0 ? 1 : 0)) * CG);
         mbar_init(smem_u32(bar_aq), 1);
         fence_barrier_init();
     } else if (warp == 1) {
-        tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+        if (CG == 2) tmem_alloc_2cta(smem_u32(tmem_slot), kTmemCols);
+        else tmem_alloc(smem_u32(tmem_slot), kTmemCols);
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // the peer's barriers exist before anything is sent to them
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t a_cols = (uint32_t)p.a_tmem_kc * 32u;  // TMEM columns of the query tile
@@ -182,22 +201,38 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
-        if (p.a_smem_kc > 0 && elect_one_sync()) {
-            mbar_arrive_expect_tx(smem_u32(bar_aq), (uint32_t)(p.a_smem_kc * kChunkBytes));
-            for (int c = 0; c < p.a_smem_kc; ++c)
-                tma_load_2d(smem_u32(a_sm + c * kChunkBytes), &tmap_q, smem_u32(bar_aq),
-                            (p.a_tmem_kc + c) * RR_TC_KCHUNK, qt * kQTile, kTmaEvictLast);
+        if (p.a_smem_kc > 0) {
+            // this CTA's query-tile tail -> its own shared memory; then tell the leader's MMA warp
+            if (elect_one_sync()) {
+                mbar_arrive_expect_tx(smem_u32(bar_aq), (uint32_t)(p.a_smem_kc * kChunkBytes));
+                for (int c = 0; c < p.a_smem_kc; ++c)
+                    tma_load_2d(smem_u32(a_sm + c * kChunkBytes), &tmap_q, smem_u32(bar_aq),
+                                (p.a_tmem_kc + c) * RR_TC_KCHUNK, qt * kQTile, kTmaEvictLast);
+            }
+            __syncwarp();
+            mbar_wait(smem_u32(bar_aq), 0);
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(bar_a), 0));
+                else mbar_arrive(smem_u32(bar_a));
+            }
         }
-        __syncwarp();
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
                 const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
                 if (elect_one_sync()) {
-                    mbar_arrive_expect_tx(smem_u32(bar_full + stage), (uint32_t)(nk * kChunkBytes));
-                    for (int c = 0; c < nk; ++c)
-                        tma_load_2d(x_base + stage * kStageBytes + c * kChunkBytes, &tmap_x,
-                                    smem_u32(bar_full + stage), (kc + c) * RR_TC_KCHUNK, tile * kNT, l2_hint);
+                    if (CG == 2) {
+                        const uint32_t full_leader = mapa_shared(smem_u32(bar_full + stage), 0);
+                        if (rank == 0) mbar_arrive_expect_tx(smem_u32(bar_full + stage), (uint32_t)(nk * kChunkBytes));
+                        for (int c = 0; c < nk; ++c)
+                            tma_load_2d_2cta(x_base + stage * kStageB + c * kChunkB, &tmap_x, full_leader,
+                                             (kc + c) * RR_TC_KCHUNK, tile * kNT + (int)rank * kRowsCta, l2_hint);
+                    } else {
+                        mbar_arrive_expect_tx(smem_u32(bar_full + stage), (uint32_t)(nk * kChunkBytes));
+                        for (int c = 0; c < nk; ++c)
+                            tma_load_2d(x_base + stage * kStageB + c * kChunkB, &tmap_x,
+                                        smem_u32(bar_full + stage), (kc + c) * RR_TC_KCHUNK, tile * kNT, l2_hint);
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -208,9 +243,9 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =======================
-        constexpr uint32_t idesc = umma_idesc_bf16(kQTile, kNT);
-        mbar_wait(smem_u32(bar_a), 0);  // the query tile is in TMEM ...
-        if (p.a_smem_kc > 0) mbar_wait(smem_u32(bar_aq), 0);  // ... and its tail in shared memory
+        constexpr uint32_t idesc = umma_idesc_bf16(kQTile * CG, kNT);
+        if (rank == 0) {  // only the leader of a pair issues
+        mbar_wait(smem_u32(bar_a), 0);  // the query tiles are in TMEM and their tails in shared memory
         tc_fence_after();
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
@@ -224,7 +259,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
-                const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageBytes) >> 4) & 0x3FFFu);
+                const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageB) >> 4) & 0x3FFFu);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(kc * 32);
                 const uint64_t a_desc =
                     kUmmaDescSw128Hi | (uint64_t)(((a_base + (kc - p.a_tmem_kc) * kChunkBytes) >> 4) & 0x3FFFu);
@@ -236,11 +271,18 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         for (int c = 0; c < kStageKc; ++c) {
                             if (c < nk) {
                                 const uint32_t at = a_tmem + c * 32;
-                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkBytes >> 4));
-                                umma_bf16_ts(d_tmem, at, bd, idesc, (uint32_t)((kc | c) != 0));
-                                umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1u);
-                                umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1u);
-                                umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1u);
+                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkB >> 4));
+                                if (CG == 2) {
+                                    umma_bf16_ts_2cta(d_tmem, at, bd, idesc, (uint32_t)((kc | c) != 0));
+                                    umma_bf16_ts_2cta(d_tmem, at + 8, bd + 2, idesc, 1u);
+                                    umma_bf16_ts_2cta(d_tmem, at + 16, bd + 4, idesc, 1u);
+                                    umma_bf16_ts_2cta(d_tmem, at + 24, bd + 6, idesc, 1u);
+                                } else {
+                                    umma_bf16_ts(d_tmem, at, bd, idesc, (uint32_t)((kc | c) != 0));
+                                    umma_bf16_ts(d_tmem, at + 8, bd + 2, idesc, 1u);
+                                    umma_bf16_ts(d_tmem, at + 16, bd + 4, idesc, 1u);
+                                    umma_bf16_ts(d_tmem, at + 24, bd + 6, idesc, 1u);
+                                }
                             }
                         }
                     } else {  // A from shared memory
@@ -248,16 +290,28 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         for (int c = 0; c < kStageKc; ++c) {
                             if (c < nk) {
                                 const uint64_t ad = a_desc + (uint64_t)(c * (kChunkBytes >> 4));
-                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkBytes >> 4));
-                                umma_bf16(d_tmem, ad, bd, idesc, 1u);
-                                umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
-                                umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
-                                umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                const uint64_t bd = b_desc + (uint64_t)(c * (kChunkB >> 4));
+                                if (CG == 2) {
+                                    umma_bf16_2cta(d_tmem, ad, bd, idesc, 1u);
+                                    umma_bf16_2cta(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                    umma_bf16_2cta(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                    umma_bf16_2cta(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                } else {
+                                    umma_bf16(d_tmem, ad, bd, idesc, 1u);
+                                    umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+                                    umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                                    umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+                                }
                             }
                         }
                     }
-                    umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
-                    if (kc + kStageKc >= p.num_kc) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
+                    if (CG == 2) {  // both CTAs' stage / accumulator barriers at once
+                        umma_commit_2cta(smem_u32(bar_empty + stage));
+                        if (kc + kStageKc >= p.num_kc) umma_commit_2cta(smem_u32(bar_acc_full + acc));
+                    } else {
+                        umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
+                        if (kc + kStageKc >= p.num_kc) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -270,6 +324,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 acc_phase ^= 1u;
             }
         }
+        }  // leader
     } else {
         // ============ warps 2..5: load the query tile into TMEM, then epilogue ============
         const int quad = warp & 3;           // TMEM lanes [32*quad, 32*quad+32) are this warp's
@@ -287,7 +342,10 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bar_a));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(bar_a), 0));
+                else mbar_arrive(smem_u32(bar_a));
+            }
         }
         float* ls_w = ls + quad * 32 * kDepth;  // this warp's 32 lists, [query][entry]
         uint32_t* lr_w = lr + quad * 32 * kDepth;
@@ -313,7 +371,10 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             // the registers hold the tile: hand the accumulator back before selecting
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(bar_acc_empty + acc));
+            if (lane == 0) {
+                if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(bar_acc_empty + acc), 0));
+                else mbar_arrive(smem_u32(bar_acc_empty + acc));
+            }
             if (++acc == p.acc_stages) {
                 acc = 0;
                 acc_phase ^= 1u;
@@ -370,10 +431,12 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all();  // neither CTA leaves while the other may still signal it
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, kTmemCols);
+        if (CG == 2) tmem_dealloc_2cta(tmem_base, kTmemCols);
+        else tmem_dealloc(tmem_base, kTmemCols);
     }
 }
 
@@ -386,16 +449,54 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
-int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk_ctl* ctl_dev, float* cand_s,
-                        uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+template <int CG>
+static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, cudaStream_t stream) {
+    const size_t stage_b = (size_t)kStageBytes / CG;
+    const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)kDepth * kQTile * 8 +
+                         (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
+    p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / stage_b);
+    const size_t smem = fixed + (size_t)p.stages * stage_b;
+    static bool attr_done[64] = {};
+    if (!attr_done[h->device & 63]) {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kSmemLimit));
+        attr_done[h->device & 63] = true;
+    }
+    // every SM gets a CTA; the kernel itself splits them into query tiles x corpus slices
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(h->sm_count / CG * CG));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG>, tx, tq, p));
+    return RR_OK;
+}
+
+int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
+                        float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
                         cudaStream_t stream) {
     RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
     RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
+    RR_REQUIRE(cta_group == 1 || cta_group == 2, "rr_gemm_scan_launch: cta_group must be 1 or 2");
+    // corpus tensor maps: 128-row boxes (shared with the small-batch kernel) or, for CTA pairs, 64-row boxes
     if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
         int rc = rr_make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, kNT);
         if (rc != RR_OK) return rc;
         h->tmap_hi_ptr = h->hi;
         h->tmap_hi_rows = h->n;
+    }
+    if (cta_group == 2 && (h->tmap_hi64_ptr != h->hi || h->tmap_hi64_rows != h->n)) {
+        int rc = rr_make_tmap_bf16_rows(&h->tmap_hi64, h->hi, h->n, h->d_pad, kNT / 2);
+        if (rc != RR_OK) return rc;
+        h->tmap_hi64_ptr = h->hi;
+        h->tmap_hi64_rows = h->n;
     }
     GemmParams p;
     p.n_rows = h->n;
@@ -405,11 +506,8 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk
     p.acc_stages = kMaxAcc;
     p.a_tmem_kc = std::min(p.num_kc, kMaxATmemKc);
     p.a_smem_kc = p.num_kc - p.a_tmem_kc;
-    const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)kDepth * kQTile * 8 +
-                         (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
-    p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / kStageBytes);
-    const size_t smem = fixed + (size_t)p.stages * kStageBytes;
-    // sibling CTAs (other query tiles, same slice) re-read each tile from L2 right away
+    p.stages = 0;
+    // sibling units (other query tiles, same slice) re-read each tile from L2 right away
     p.l2_hint = kTmaEvictFirst;
     p.l2_hint_shared = kTmaEvictNormal;
     p.qbf16 = qbf16_dev;
@@ -419,19 +517,11 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, rr_chunk
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
     RR_REQUIRE((int64_t)h->sm_count * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kSmemLimit));
-        attr_done[h->device & 63] = true;
-    }
     // the tail of each query tile is fetched by TMA from the bf16 query buffer
-    const int nq_rows = (nq + kQTile - 1) / kQTile * kQTile;
+    const int q_align = kQTile * cta_group;
+    const int nq_rows = (nq + q_align - 1) / q_align * q_align;
     alignas(64) CUtensorMap tq;
     int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, nq_rows, h->d_pad, kQTile);
     if (rc != RR_OK) return rc;
-    // every SM gets a CTA; the kernel itself splits them into query tiles x corpus slices
-    rr_gemm_scan_kernel<<<h->sm_count, kThreads, smem, stream>>>(h->tmap_hi, tq, p);
-    RR_CUDA_CHECK(cudaGetLastError());
-    return RR_OK;
+    return cta_group == 2 ? launch_cg<2>(h, h->tmap_hi64, tq, p, stream) : launch_cg<1>(h, h->tmap_hi, tq, p, stream);
 }

@@ -236,22 +236,25 @@ def test_errors_like_faiss(faiss):
 
 
 # ---------------------------------------------------------------------------
-# Large-batch path (rr_scan_gemm.cu: queries stationary in TMEM).  "scan_path" 2
-# forces it for any batch size so that small cases reach it too.
+# Large-batch path (rr_scan_gemm.cu: queries stationary in TMEM).  "scan_path" 2 (one CTA
+# per 128-query tile) / 3 (CTA pairs, tcgen05 cta_group::2, 256 queries per pair) force it for
+# any batch size so that small cases reach it too.
 # ---------------------------------------------------------------------------
-def _gemm_index(faiss, xb):
+def _gemm_index(faiss, xb, path=2):
     ix = _index(faiss, xb, "auto")
-    ix.set_param("scan_path", 2)
+    ix.set_param("scan_path", path)
     return ix
 
 
+@pytest.mark.parametrize("path", [2, 3])
 @pytest.mark.parametrize("n,d,k,nq", [(5000, 768, 32, 5), (20000, 768, 32, 130), (4000, 384, 10, 64),
-                                      (2500, 100, 7, 2), (63, 768, 32, 3), (9000, 512, 10, 257)])
-def test_gemm_path_vs_oracle(faiss, n, d, k, nq):
+                                      (2500, 100, 7, 2), (63, 768, 32, 3), (9000, 512, 10, 257),
+                                      (7000, 640, 10, 300)])
+def test_gemm_path_vs_oracle(faiss, n, d, k, nq, path):
     rng = np.random.default_rng(n + d + nq)
     xb = rng.standard_normal((n, d), dtype=np.float32)
     q = rng.standard_normal((nq, d), dtype=np.float32)
-    ix = _gemm_index(faiss, xb)
+    ix = _gemm_index(faiss, xb, path)
     D, I = ix.search(q, k)
     Dr, Ir = oracle.search(q, xb, k)
     oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
@@ -264,11 +267,11 @@ def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
     the exact rescan would hide a broken tensor-core kernel), for 1, 2 and 8 query tiles."""
     d, k = 768, 32
     xb = syn.corpus_rows(2, 70000, d)
-    for nq in (100, 256, 1024):
+    for nq, path in ((100, 2), (100, 3), (256, 2), (256, 3), (1024, 2), (1024, 3), (700, 3)):
         q = syn.queries(nq, d, [2], seed=nq)
-        ix = _gemm_index(faiss, xb)
+        ix = _gemm_index(faiss, xb, path)
         D, I = ix.search(q, k)
-        assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data: {ix.stats()}"
+        assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data (path {path}): {ix.stats()}"
         ixs = _index(faiss, xb, "auto")
         ixs.set_param("scan_path", 1)
         Ds, Is = ixs.search(q, k)
