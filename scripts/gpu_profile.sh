@@ -1,17 +1,22 @@
 #!/bin/bash
-# ncu evidence for the dominant kernel (one GPU).  Usage: bash scripts/gpu_profile.sh <tag>
+# ncu evidence for the dominant kernels (one GPU).  Usage: bash scripts/gpu_profile.sh <tag>
 # 1) launch list (gpu__time_duration per launch of every rr_* kernel) of the default bench command, short
-# 2) --set full capture of the scan kernel on a PubMed-shaped slice (6M x 768, >> L2)
+# 2) --set full capture of the large-batch scan kernel (CTA pairs) on a PubMed-shaped slice (6M x 768, >> L2), batch 1024
+# 3) --set full capture of the small-batch scan kernel on the same slice, batch 64
 TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD1="python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+CMD1="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sweep 64"
 $CMD1 > gpurun_out/${TAG}_plain1.json 2> gpurun_out/${TAG}_plain1.err &&
-ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 400 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 600 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD1 > gpurun_out/${TAG}_ncu1.out 2>&1
 echo "launch list exit=$?"
-CMD2="python bench.py --workload pubmed --rows-scale 0.25 --steps 3 --warmup 3 --no-cpu-baseline"
+CMD2="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 1024 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD2 > gpurun_out/${TAG}_plain2.json 2> gpurun_out/${TAG}_plain2.err &&
-ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 -c 2 \
-    -f -o gpurun_out/${TAG}_scan $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
-echo "full capture exit=$?"
-ls -la gpurun_out/
+ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 3 -c 1 \
+    -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
+echo "gemm capture exit=$?"
+CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
+$CMD3 > gpurun_out/${TAG}_plain3.json 2> gpurun_out/${TAG}_plain3.err &&
+ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 -c 1 \
+    -f -o gpurun_out/${TAG}_scan $CMD3 > gpurun_out/${TAG}_ncu3.out 2>&1
+echo "scan capture exit=$?"
