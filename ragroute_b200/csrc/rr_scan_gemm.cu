@@ -22,10 +22,13 @@
 //   * two accumulator stages of 128 fp32 columns (128 queries x 128 corpus rows each);
 //   * epilogue orientation: TMEM lane = query, so every epilogue THREAD owns one query:
 //     its running threshold sits in a register and the 128 scores of a tile cost one max
-//     tree + one compare.  Survivors are inserted WARP-COOPERATIVELY into that query's
-//     unsorted top-32 list in shared memory (lane e holds entry e; replace-the-minimum
-//     with three redux.sync), about 40 cycles per insert and no divergence -- a per-thread
-//     sorted insert measured ~2000 cycles and made the epilogue the bottleneck.
+//     tree + one compare.  Survivors are first appended (predicated stores, no branches)
+//     to the thread's small pending queue in shared memory, then drained in SIMT ROUNDS:
+//     in one round every thread with a pending survivor overwrites the minimum of its own
+//     unsorted top-32 list and rescans the list for the new minimum (32 independent
+//     loads) -- one round serves all 32 queries of the warp at once.  Measured insert
+//     costs that made the epilogue the bottleneck before: per-thread SORTED insert ~2000
+//     cycles, warp-cooperative replace-the-minimum ~245 cycles per insert (serial).
 // CTA c works on query tile (c % nqt) and corpus slice (c / nqt): the nqt CTAs that share
 // a slice stream the same rows at the same time, so HBM is read once and the other
 // nqt - 1 reads hit L2.
@@ -34,7 +37,6 @@
 
 #include "rr_index_internal.cuh"
 #include "rr_ptx.cuh"
-#include "rr_topm.cuh"
 
 namespace {
 using namespace rr_ptx;
@@ -71,42 +73,41 @@ struct GemmParams {
     int64_t cand_stride;
 };
 
-// Warp-cooperative insert of (v, row) into the unsorted top-kDepth list of one query
-// (entries at lsp[0..31], lane e owns entry e): the worst entry -- lowest score, then
-// highest row; an empty slot is (-inf, RR_NO_ROW) and therefore always worst -- is
-// replaced.  Returns the list's new minimum score = the query's new threshold (-inf
-// while an empty slot remains).  The caller guarantees v > current minimum.
-__device__ __forceinline__ float coop_insert(float* lsp, uint32_t* lrp, float v, uint32_t row, int lane) {
-    static_assert(kDepth == 32, "one list entry per lane");
-    const float es = lsp[lane];
-    const uint32_t er = lrp[lane];
-    uint32_t key = rr_float_key(es);
-    const uint32_t kmin = __reduce_min_sync(RR_FULL, key);
-    const uint32_t rmax = __reduce_max_sync(RR_FULL, (key == kmin) ? er : 0u);
-    const unsigned cand = __ballot_sync(RR_FULL, key == kmin && er == rmax);
-    if (lane == __ffs(cand) - 1) {
-        lsp[lane] = v;
-        lrp[lane] = row;
-        key = rr_float_key(v);
+// Per-thread state: unsorted top-kDepth list of the thread's query in shared memory, entry e of
+// thread t at [e * kQTile + t] (conflict-free across a warp); `thr` = the list's minimum score
+// (-inf while an empty slot remains), `pos` = where that minimum sits.
+// Drain the pending queues of a warp: round i inserts the i-th pending survivor of every thread
+// that has one.  Out of line: it runs for a fraction of the tiles.
+constexpr int kPend = 16;  // pending slots per thread
+
+__device__ __noinline__ void epi_drain(int cnt, float& thr, int& pos, float* ls, uint32_t* lr, const float* ps,
+                                       const uint32_t* pr, int t) {
+    int i = 0;
+    while (__any_sync(RR_FULL, i < cnt)) {
+        if (i < cnt) {
+            const float v = ps[i * kQTile + t];
+            if (v > thr) {  // an earlier insert of this drain may have raised the threshold
+                ls[pos * kQTile + t] = v;
+                lr[pos * kQTile + t] = pr[i * kQTile + t];
+                float m = ls[t];
+                int am = 0;
+#pragma unroll
+                for (int e = 1; e < kDepth; ++e) {
+                    const float sv = ls[e * kQTile + t];
+                    if (sv < m) {
+                        m = sv;
+                        am = e;
+                    }
+                }
+                thr = m;
+                pos = am;
+            }
+        }
+        ++i;
     }
     __syncwarp();
-    return rr_key_float(__reduce_min_sync(RR_FULL, key));
 }
 
-// One column of the tile: lanes whose score beats their own threshold hand it to the warp.
-// Out of line: it runs for a small fraction of the columns, and 128 inlined copies would not
-// fit the instruction cache.
-__device__ __noinline__ float epi_take(unsigned b, float v, uint32_t row, float thr, float* ls_w, uint32_t* lr_w,
-                                       int lane) {
-    while (b) {
-        const int src = __ffs(b) - 1;
-        b &= b - 1;
-        const float cv = __shfl_sync(RR_FULL, v, src);
-        const float nt = coop_insert(ls_w + src * kDepth, lr_w + src * kDepth, cv, row, lane);
-        if (lane == src) thr = nt;
-    }
-    return thr;
-}
 static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA box of the hi plane");
 
 // CG = 1: one CTA per work unit (128 queries x 128-row corpus tiles).
@@ -149,9 +150,11 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                                                ~(uintptr_t)1023);
     uint8_t* x_sm = base;
     uint8_t* a_sm = x_sm + p.stages * kStageB;  // [a_smem_kc][128 queries x 64 k], 128B swizzle
-    float* ls = reinterpret_cast<float*>(a_sm + p.a_smem_kc * kChunkBytes);  // [128 queries][kDepth]
+    float* ls = reinterpret_cast<float*>(a_sm + p.a_smem_kc * kChunkBytes);  // lists   [kDepth][128 queries]
     uint32_t* lr = reinterpret_cast<uint32_t*>(ls + kDepth * kQTile);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lr + kDepth * kQTile);
+    float* ps = reinterpret_cast<float*>(lr + kDepth * kQTile);              // pending [kPend][128 queries]
+    uint32_t* pr = reinterpret_cast<uint32_t*>(ps + kPend * kQTile);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pr + kPend * kQTile);
     uint64_t* bar_full = bars;
     uint64_t* bar_empty = bars + kMaxStages;
     uint64_t* bar_acc_full = bars + 2 * kMaxStages;
@@ -347,14 +350,13 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 else mbar_arrive(smem_u32(bar_a));
             }
         }
-        float* ls_w = ls + quad * 32 * kDepth;  // this warp's 32 lists, [query][entry]
-        uint32_t* lr_w = lr + quad * 32 * kDepth;
-        for (int i = lane; i < 32 * kDepth; i += 32) {
-            ls_w[i] = RR_NEG_INF;
-            lr_w[i] = RR_NO_ROW;
+        for (int e = 0; e < kDepth; ++e) {
+            ls[e * kQTile + t] = RR_NEG_INF;
+            lr[e * kQTile + t] = RR_NO_ROW;
         }
-        __syncwarp();
         float thr = (qg < n_active) ? RR_NEG_INF : __builtin_huge_valf();
+        int pos = 0;  // slot of the list's minimum (an empty slot while there is one)
+        int cnt = 0;  // pending survivors
 
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -407,26 +409,43 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 #pragma unroll
                 for (int g = 0; g < 16; ++g) {
                     if (__any_sync(RR_FULL, m8[g] > thr)) {
+                        // append this group's survivors to the pending queue (predicated, branch-free)
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             const float v = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
-                            const unsigned hb = __ballot_sync(RR_FULL, v > thr);
-                            if (hb) thr = epi_take(hb, v, (uint32_t)(row0 + g * 8 + j), thr, ls_w, lr_w, lane);
+                            if (v > thr) {
+                                ps[cnt * kQTile + t] = v;
+                                pr[cnt * kQTile + t] = (uint32_t)(row0 + g * 8 + j);
+                                ++cnt;
+                            }
+                        }
+                        // a group adds at most 8 entries per thread: drain before the queue could overflow
+                        if (__any_sync(RR_FULL, cnt > kPend - 8)) {
+                            epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                            cnt = 0;
                         }
                     }
                 }
+                // one drain per tile serves every query of the warp that had survivors
+                if (__any_sync(RR_FULL, cnt > 0)) {
+                    epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                    cnt = 0;
+                }
             }
         }
-        // publish sorted: [query][list = slice][kDepth], lane e writes entry e
-        for (int i = 0; i < 32; ++i) {
-            const int qi = qt * kQTile + quad * 32 + i;
-            if (qi >= n_active) break;
-            float es = ls_w[i * kDepth + lane];
-            uint32_t er = lr_w[i * kDepth + lane];
-            rr_warp_sort(es, er, lane);
-            const int64_t o = (int64_t)qi * p.cand_stride + (int64_t)slice * kDepth + lane;
-            p.cand_s[o] = es;
-            p.cand_r[o] = er;
+        // publish [compact query][list = slice][kDepth]: the list's minimum goes to the LAST slot (the tail
+        // that bounds every dropped row; an empty slot there = nothing was dropped), the rest unsorted
+        if (qg < n_active) {
+            const int64_t o = (int64_t)qg * p.cand_stride + (int64_t)slice * kDepth;
+            int w = 0;
+            for (int e = 0; e < kDepth; ++e) {
+                if (e == pos) continue;
+                p.cand_s[o + w] = ls[e * kQTile + t];
+                p.cand_r[o + w] = lr[e * kQTile + t];
+                ++w;
+            }
+            p.cand_s[o + kDepth - 1] = ls[pos * kQTile + t];
+            p.cand_r[o + kDepth - 1] = lr[pos * kQTile + t];
         }
     }
 
@@ -452,7 +471,7 @@ int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 template <int CG>
 static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, cudaStream_t stream) {
     const size_t stage_b = (size_t)kStageBytes / CG;
-    const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)kDepth * kQTile * 8 +
+    const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
                          (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
     p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / stage_b);
     const size_t smem = fixed + (size_t)p.stages * stage_b;
