@@ -177,11 +177,12 @@ rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict
                      int qsub, float* __restrict__ cand_s,
                      uint32_t* __restrict__ cand_r, int64_t cand_stride) {
     const int n_fail = ctl->n_fail;
-    const int q0 = (int)blockIdx.y * qsub;  // blockIdx.y = sub-batch of failing queries
-    if (q0 >= n_fail) return;
-    const int nq = min(qsub, n_fail - q0);
     constexpr int M = RR_EXACT_LIST_DEPTH;
     constexpr int W = RR_EXACT_WARPS;
+    // sub-batches of failing queries are strided over gridDim.y (a few rows of blocks suffice:
+    // normally nothing failed and every block leaves here at once)
+    for (int q0 = (int)blockIdx.y * qsub; q0 < n_fail; q0 += (int)gridDim.y * qsub) {
+    const int nq = min(qsub, n_fail - q0);
 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* qs = reinterpret_cast<float*>(smem_raw);                       // [qsub][d_pad]
@@ -275,6 +276,8 @@ rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict
         const int64_t o = (int64_t)qid[j] * cand_stride + (int64_t)blockIdx.x * M + lane;
         cand_s[o] = es;
         cand_r[o] = er;
+    }
+    __syncthreads();  // shared memory is reused by the next sub-batch
     }
 }
 
@@ -477,33 +480,49 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     __syncthreads();
 
     if (RESCORE) {
-        // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation
-        for (int i = w; i < kp; i += RR_FIN_THREADS / 32) {
-            const int64_t row = sel_r[i];
-            const uint4* hrow = reinterpret_cast<const uint4*>(a.hi + row * a.d_pad);
-            const uint4* lrow = reinterpret_cast<const uint4*>(a.lo + row * a.d_pad);
-            double acc = 0.0;
+        // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation.  One warp per row,
+        // RB rows per warp in flight at once (the gathers are random 2 x d_pad*2-byte reads: latency-bound)
+        constexpr int RB = 4;
+        constexpr int NW = RR_FIN_THREADS / 32;
+        for (int i0 = w * RB; i0 < kp; i0 += NW * RB) {
+            double acc[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) acc[r] = 0.0;
             for (int e0 = lane * 8; e0 < a.d_pad; e0 += 256) {
-                const uint4 hv = __ldg(hrow + (e0 >> 3));
-                const uint4 lv = __ldg(lrow + (e0 >> 3));
+                uint4 hv[RB], lv[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    const int i = min(i0 + r, kp - 1);
+                    const int64_t row = sel_r[i];
+                    hv[r] = __ldg(reinterpret_cast<const uint4*>(a.hi + row * a.d_pad) + (e0 >> 3));
+                    lv[r] = __ldg(reinterpret_cast<const uint4*>(a.lo + row * a.d_pad) + (e0 >> 3));
+                }
                 const float4 qa = *reinterpret_cast<const float4*>(q_sm + e0);
                 const float4 qb = *reinterpret_cast<const float4*>(q_sm + e0 + 4);
-                float2 t;
-                t = rr_join_f32x2(hv.x, lv.x);
-                acc = fma((double)t.x, (double)qa.x, acc);
-                acc = fma((double)t.y, (double)qa.y, acc);
-                t = rr_join_f32x2(hv.y, lv.y);
-                acc = fma((double)t.x, (double)qa.z, acc);
-                acc = fma((double)t.y, (double)qa.w, acc);
-                t = rr_join_f32x2(hv.z, lv.z);
-                acc = fma((double)t.x, (double)qb.x, acc);
-                acc = fma((double)t.y, (double)qb.y, acc);
-                t = rr_join_f32x2(hv.w, lv.w);
-                acc = fma((double)t.x, (double)qb.z, acc);
-                acc = fma((double)t.y, (double)qb.w, acc);
+#pragma unroll
+                for (int r = 0; r < RB; ++r) {
+                    double s_ = acc[r];
+                    float2 t;
+                    t = rr_join_f32x2(hv[r].x, lv[r].x);
+                    s_ = fma((double)t.x, (double)qa.x, s_);
+                    s_ = fma((double)t.y, (double)qa.y, s_);
+                    t = rr_join_f32x2(hv[r].y, lv[r].y);
+                    s_ = fma((double)t.x, (double)qa.z, s_);
+                    s_ = fma((double)t.y, (double)qa.w, s_);
+                    t = rr_join_f32x2(hv[r].z, lv[r].z);
+                    s_ = fma((double)t.x, (double)qb.x, s_);
+                    s_ = fma((double)t.y, (double)qb.y, s_);
+                    t = rr_join_f32x2(hv[r].w, lv[r].w);
+                    s_ = fma((double)t.x, (double)qb.z, s_);
+                    s_ = fma((double)t.y, (double)qb.w, s_);
+                    acc[r] = s_;
+                }
             }
-            acc = rr_warp_sum(acc);
-            if (lane == 0) sel_s[i] = (float)acc;
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const double tot = rr_warp_sum(acc[r]);
+                if (lane == 0 && i0 + r < kp) sel_s[i0 + r] = (float)tot;
+            }
         }
         __syncthreads();
     }
@@ -967,7 +986,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     RR_REQUIRE(ex_smem <= (200u << 10), "dimension %d too large for the exact scan kernel", h->d);
     if (h->n > 0) {
         // one launch covers every sub-batch; blocks beyond the failing queries exit at once
-        const dim3 grid((unsigned)g_exact, (unsigned)((nq + qsub - 1) / qsub));
+        const dim3 grid((unsigned)g_exact, (unsigned)std::min(4, (nq + qsub - 1) / qsub));
         rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
             h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, fail_list, ctl, qsub, cand_s, cand_r, cand_stride);
         RR_CUDA_CHECK(cudaGetLastError());

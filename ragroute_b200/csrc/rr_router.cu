@@ -107,18 +107,16 @@ __global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a)
         for (int qb = 0; qb < kQB; ++qb) acc[qb] = 0.f;
         const float* wp = a.w1t + t;
         int j = j_lo;
-        for (; j + 4 <= j_hi; j += 4) {
-            const float w0 = __ldg(wp + (size_t)(j + 0) * kH1);
-            const float w1 = __ldg(wp + (size_t)(j + 1) * kH1);
-            const float w2 = __ldg(wp + (size_t)(j + 2) * kH1);
-            const float w3 = __ldg(wp + (size_t)(j + 3) * kH1);
+        // 8 independent weight loads in flight per thread: the loop is L2-latency-bound
+        for (; j + 8 <= j_hi; j += 8) {
+            float wv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
 #pragma unroll
             for (int qb = 0; qb < kQB; ++qb) {
                 const float* xr = xq + (size_t)qb * a.d_in + j;
-                acc[qb] = fmaf(w0, xr[0], acc[qb]);
-                acc[qb] = fmaf(w1, xr[1], acc[qb]);
-                acc[qb] = fmaf(w2, xr[2], acc[qb]);
-                acc[qb] = fmaf(w3, xr[3], acc[qb]);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
             }
         }
         for (; j < j_hi; ++j) {

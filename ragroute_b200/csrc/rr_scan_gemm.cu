@@ -335,12 +335,19 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int qg = qt * kQTile + t;      // query inside the chunk
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         {
+            // each thread copies its own query row (a_cols * 4 bytes) into its TMEM lane; 8 x 16-byte
+            // loads in flight per thread (a_cols is a multiple of 32: whole K-chunks)
             const uint4* src = reinterpret_cast<const uint4*>(p.qbf16 + (size_t)qg * p.d_pad);
-            for (uint32_t c = 0; c < a_cols; c += 8) {
-                const uint4 v0 = __ldg(src + (c >> 2));
-                const uint4 v1 = __ldg(src + (c >> 2) + 1);
-                const uint32_t r[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                tmem_st_x8(lane_addr + c, r);
+            for (uint32_t c = 0; c < a_cols; c += 32) {
+                uint4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (c >> 2) + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t r[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                           v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                    tmem_st_x8(lane_addr + c + 8 * u, r);
+                }
             }
             tmem_st_wait();
             tc_fence_before();
