@@ -284,6 +284,8 @@ def gpu_main(args, rows, workload):
     sids = [syn.MEDRAG_SOURCE_TO_ID[n] for n in names]
     for ix in fed.indexes:
         ix.set_param("profile", 1)
+        if args.scan_path:
+            ix.set_param("scan_path", args.scan_path)
 
     def barrier():
         if world > 1:
@@ -362,13 +364,13 @@ def gpu_main(args, rows, workload):
 
     def roofline_of(run: dict, batch: int) -> dict:
         """Roofline entry of the dominant kernel of a run (rank 0's launches, CUDA events on the
-        launching stream).  batch <= 64: the swap-AB scan, HBM-bound (intensity = batch flop/byte);
-        larger batches: the queries-in-TMEM scan, bound by the bf16 tensor pipe."""
+        launching stream).  batch <= 256 (at most ~128 routed queries per source): HBM-bound, the
+        intensity over the bf16 plane is below the ridge; larger batches: bound by the bf16 tensor pipe."""
         n = run["scan_launches"]
         if not n:
             return {"bound": None, "achieved": None, "peak": None, "frac": None, "traffic": None}
-        small = batch <= 64
-        key = "rr_tc_scan_kernel" if small else "rr_gemm_scan_kernel"
+        small = batch <= 256  # one 128-query tile per CTA or the swap-AB scan: HBM-bound
+        key = "rr_tc_scan_kernel" if (batch <= 48 and args.scan_path == 0) or args.scan_path == 1 else "rr_gemm_scan_kernel"
         tj = traffic_db.get(key, {})
         traffic = tj.get("dram_over_algorithmic", 0) * run["scan_bytes"] / n if tj else None
         common = {"kernel": key, "launches_timed": n, "avg_launch_ms": run["scan_ms"] / n,
@@ -474,7 +476,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto"] + list(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=1024,
+    ap.add_argument("--batch", type=int, default=2048,
                     help="queries per step; <= 64 is the HBM-bound regime, >= 128 the tensor-bound one")
     ap.add_argument("--routing", default="ragroute", choices=["ragroute", "all"])
     ap.add_argument("--rows-scale", type=float, default=1.0, help="scale every source's row count (debug)")
@@ -482,6 +484,8 @@ def main():
     ap.add_argument("--sweep-ms-budget", type=float, default=1500.0)
     ap.add_argument("--cpu-sample-rows", type=int, default=600_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scan-path", type=int, default=0,
+                    help="debug: force a scan kernel (1 = 64-query passes, 2 = large-batch, 3 = large-batch CTA pairs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] warmup raised to 3 (timing rule)")

@@ -93,27 +93,48 @@ rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
     }
 }
 
-// Large-batch path: compact the ROUTED queries of a chunk (<= 1024) to the front.  cpos[b] = row of
-// query b in the bf16 query buffer: routed queries keep their order in [0, n_active), unrouted ones
-// follow in [n_active, nq) (their rows are zero).  One block of 1024 threads.
+// Large-batch path: compact the ROUTED queries of a chunk (<= RR_GEMM_QCHUNK) to the front.  cpos[b] =
+// row of query b in the bf16 query buffer: routed queries keep their order in [0, n_active), unrouted
+// ones follow in [n_active, nq) (their rows are zero).  One block of 1024 threads, kCompactPer
+// consecutive queries per thread.
+constexpr int kCompactPer = RR_GEMM_QCHUNK / 1024;
+static_assert(RR_GEMM_QCHUNK % 1024 == 0 && kCompactPer >= 1 && kCompactPer <= 8, "compaction block covers the chunk");
+
 __global__ void __launch_bounds__(1024)
 rr_compact_queries_kernel(const uint8_t* __restrict__ mask, int64_t mask_stride, int nq, int* __restrict__ cpos,
                           rr_chunk_ctl* ctl) {
     __shared__ int warp_cnt[32];
-    const int b = threadIdx.x, lane = b & 31, w = b >> 5;
-    const bool act = (b < nq) && (mask ? (mask[(int64_t)b * mask_stride] != 0) : true);
-    const unsigned bal = __ballot_sync(RR_FULL, act);
-    if (lane == 0) warp_cnt[w] = __popc(bal);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    bool act[kCompactPer];
+    int mine = 0;
+#pragma unroll
+    for (int u = 0; u < kCompactPer; ++u) {
+        const int b = tid * kCompactPer + u;
+        act[u] = (b < nq) && (mask ? (mask[(int64_t)b * mask_stride] != 0) : true);
+        mine += act[u] ? 1 : 0;
+    }
+    // exclusive prefix of `mine` over the block
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(RR_FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_cnt[w] = incl;
     __syncthreads();
-    int before = 0, total = 0;
+    int before = incl - mine, total = 0;
     for (int i = 0; i < 32; ++i) {
         const int c = warp_cnt[i];
         if (i < w) before += c;
         total += c;
     }
-    before += __popc(bal & ((1u << lane) - 1u));
-    if (b < nq) cpos[b] = act ? before : total + (b - before);
-    if (b == 0) ctl->n_active = total;
+#pragma unroll
+    for (int u = 0; u < kCompactPer; ++u) {
+        const int b = tid * kCompactPer + u;
+        if (b < nq) cpos[b] = act[u] ? before : total + (b - before);
+        before += act[u] ? 1 : 0;
+    }
+    if (tid == 0) ctl->n_active = total;
 }
 
 // fp32 queries -> bf16 tile rows (zero padded to d_pad; rows >= nq zeroed), norms,
@@ -818,17 +839,22 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
 
 static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Large-batch path: more than one 64-query pass and a dimension whose query tile fits TMEM.
+// Kernel dispatch (measured on B200, full and 1/8-scale MedRAG federation, scripts/gpu_pathcmp*.sh):
+//   nq <= 48            swap-AB scan (rr_scan_tc.cu): lowest fixed cost, HBM-bound
+//   48 < nq <= 256      queries-in-TMEM scan, one CTA per 128-query tile: still HBM-bound, but its
+//                       per-thread epilogue keeps up when shards are small (many survivors per tile)
+//   nq > 256            the same on CTA pairs (tensor-bound regime)
+// Dimensions whose query tile does not fit TMEM + shared memory (d_pad > 768) always take the
+// swap-AB scan in passes of <= 64 queries.
 static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
     if (!rr_gemm_scan_supported(h) || h->scan_path == RR_PATH_SMALL) return false;
     if (h->scan_path == RR_PATH_GEMM || h->scan_path == RR_PATH_GEMM_PAIR) return true;
-    return nq > RR_TC_MAX_QTILE;
+    return nq > 48;
 }
-// CTA pairs (256 queries per work unit) pay off once a chunk has more than one 128-query tile
 static int rr_gemm_cta_group(const rr_index* h, int nq) {
     if (h->scan_path == RR_PATH_GEMM) return 1;
     if (h->scan_path == RR_PATH_GEMM_PAIR) return 2;
-    return nq > RR_GEMM_QTILE ? 2 : 1;
+    return nq > 2 * RR_GEMM_QTILE ? 2 : 1;
 }
 
 // one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch path) queries

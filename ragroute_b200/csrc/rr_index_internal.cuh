@@ -19,7 +19,7 @@ constexpr int RR_QCHUNK = 256;         // queries handled per internal chunk (64
 constexpr int RR_GEMM_TILE_ROWS = 128; // corpus rows per MMA in the large-batch kernel (UMMA N)
 constexpr int RR_GEMM_QTILE = 128;     // queries per CTA in the large-batch kernel (UMMA M, TMEM lanes)
 constexpr int RR_GEMM_LIST_DEPTH = 32; // entries per (CTA, query) list of the large-batch kernel
-constexpr int RR_GEMM_QCHUNK = 1024;   // queries per chunk on the large-batch path
+constexpr int RR_GEMM_QCHUNK = 2048;   // queries per chunk on the large-batch path
 constexpr int RR_PATH_AUTO = 0, RR_PATH_SMALL = 1, RR_PATH_GEMM = 2, RR_PATH_GEMM_PAIR = 3;  // set_param "scan_path"
 constexpr int RR_EXACT_MAX_QSUB = 16;  // queries per exact-scan launch
 

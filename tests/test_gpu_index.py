@@ -267,7 +267,7 @@ def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
     the exact rescan would hide a broken tensor-core kernel), for 1, 2 and 8 query tiles."""
     d, k = 768, 32
     xb = syn.corpus_rows(2, 70000, d)
-    for nq, path in ((100, 2), (100, 3), (256, 2), (256, 3), (1024, 2), (1024, 3), (700, 3)):
+    for nq, path in ((100, 2), (100, 3), (256, 2), (256, 3), (1024, 2), (1024, 3), (700, 3), (2048, 3), (60, 0), (200, 0)):
         q = syn.queries(nq, d, [2], seed=nq)
         ix = _gemm_index(faiss, xb, path)
         D, I = ix.search(q, k)
@@ -284,15 +284,15 @@ def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
 def test_gemm_path_mask_chunks_and_default_dispatch(faiss):
     d, k = 768, 10
     xb = syn.corpus_rows(1, 30000, d)
-    q = syn.queries(1100, d, [1], seed=12)     # > 1024: two chunks on the large-batch path
+    q = syn.queries(2300, d, [1], seed=12)     # > 2048: two chunks on the large-batch path
     ix = _index(faiss, xb, "auto")             # default dispatch: nq > 64 takes the large-batch path
     qt = torch.from_numpy(q).cuda()
-    mask = (torch.arange(1100, device="cuda") % 3 != 0).to(torch.uint8).reshape(-1, 1).contiguous()
+    mask = (torch.arange(2300, device="cuda") % 3 != 0).to(torch.uint8).reshape(-1, 1).contiguous()
     D, I = ix.search_tensor(qt, k, mask=mask)
     torch.cuda.synchronize()
     D, I = D.cpu().numpy(), I.cpu().numpy()
     assert ix.stats()["exact_rescans"] == 0
-    off = (np.arange(1100) % 3 == 0)
+    off = (np.arange(2300) % 3 == 0)
     assert (I[off] == -1).all() and (D[off] == -FLT_MAX).all()
     sel = np.nonzero(~off)[0][::37]
     Dr, Ir = oracle.search(q[sel], xb, k)
