@@ -52,3 +52,110 @@ def test_routing_strategies(cuda_required, routing):
         assert (got_i[b, n_ref:] == -1).all()
     with pytest.raises(ValueError):
         Federation(sources, k, routing="bogus")
+
+
+# FeB4RAG shape (config.py:34,44-58,72-86,94,99): 13 sources, 8 query encoders of 768 / 1024 / 4096
+# dims, EMBEDDING_MAX_LENGTH 4096, router in_dim 2*4096 + 13 = 8205, no scaler, threshold 0.5, k = 10.
+_FEB_SOURCES = ["msmarco", "trec-covid", "nfcorpus", "scidocs", "nq", "hotpotqa", "fiqa", "arguana",
+                "webis-touche2020", "dbpedia-entity", "fever", "climate-fever", "scifact"]
+_FEB_MODEL = {"msmarco": "e5-large", "trec-covid": "SGPT-5.8B", "nfcorpus": "UAE-Large-V1",
+              "scidocs": "all-mpnet-base-v2", "nq": "multilingual-e5-large", "hotpotqa": "ember-v1",
+              "fiqa": "all-mpnet-base-v2", "arguana": "UAE-Large-V1", "webis-touche2020": "e5-base",
+              "dbpedia-entity": "UAE-Large-V1", "fever": "UAE-Large-V1", "climate-fever": "UAE-Large-V1",
+              "scifact": "gte-base"}
+_FEB_DIM = {"e5-large": 1024, "SGPT-5.8B": 4096, "UAE-Large-V1": 1024, "all-mpnet-base-v2": 768,
+            "multilingual-e5-large": 1024, "ember-v1": 1024, "e5-base": 768, "gte-base": 768}
+_FEB_ID = {"arguana": 0, "climate-fever": 1, "dbpedia-entity": 2, "fever": 3, "fiqa": 4, "hotpotqa": 5,
+           "msmarco": 6, "nfcorpus": 7, "nq": 8, "scidocs": 9, "scifact": 10, "trec-covid": 11,
+           "webis-touche2020": 12}
+
+
+def test_feb4rag_shaped_federation(cuda_required):
+    """Mixed-dimension sources (768 / 1024 / 4096: the 4096-d one takes the swap-AB scan in
+    16-query passes), several encoders, no scaler: router mask and per-source top-10 against the oracle."""
+    from oracle import flat_ip, router_ref
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation
+    from ragroute_b200.router import FusedCorpusRouter
+    d_max, k, B, S = 4096, 10, 70, 13
+    rng = np.random.default_rng(5)
+    corpora, centroids = {}, {}
+    for i, n in enumerate(_FEB_SOURCES):
+        d = _FEB_DIM[_FEB_MODEL[n]]
+        mu = rng.standard_normal(d).astype(np.float32) * np.float32(0.5 / np.sqrt(d))
+        corpora[n] = (rng.standard_normal((700 + 90 * i, d), dtype=np.float32) / np.float32(np.sqrt(d)) + mu)
+        centroids[n] = np.pad(corpora[n].mean(axis=0), (0, d_max - d)).astype(np.float32)   # router.py:149-151
+    models = sorted(set(_FEB_MODEL.values()))
+    q_by_model = {m: (rng.standard_normal((B, _FEB_DIM[m]), dtype=np.float32) / np.float32(np.sqrt(_FEB_DIM[m])))
+                  for m in models}
+    in_dim = 2 * d_max + S
+    sd = syn.router_state_dict(in_dim, 3)
+    router = FusedCorpusRouter(in_dim)
+    router.load_state_dict(sd)
+    router.set_tables(_FEB_SOURCES, d_max, _FEB_MODEL, centroids, _FEB_ID, S, scaler=None)
+    # calibrate fc3.bias so that about half the pairs are routed
+    q_router = np.zeros((B, len(router.slot_names), d_max), dtype=np.float32)
+    for si, m in enumerate(router.slot_names):
+        q_router[:, si, :_FEB_DIM[m]] = q_by_model[m]
+    qr = torch.from_numpy(q_router).cuda()
+    _, lg = router.select(qr, 0.5, return_logits=True)
+    sd = dict(sd)
+    sd["fc3.bias"] = (sd["fc3.bias"] - np.float32(lg.median().item())).astype(np.float32)
+    router.load_state_dict(sd)
+    router.set_tables(_FEB_SOURCES, d_max, _FEB_MODEL, centroids, _FEB_ID, S, scaler=None)
+
+    sources = {}
+    for n in _FEB_SOURCES:
+        ix = IndexFlatIP(corpora[n].shape[1])
+        ix.add(corpora[n])
+        sources[n] = ix
+    fed = Federation(sources, k, router=router, routing="ragroute", threshold=0.5, dataset="feb4rag")
+    mask = fed.route(qr)
+    q_list = [torch.from_numpy(q_by_model[_FEB_MODEL[n]]).cuda() for n in _FEB_SOURCES]
+    D_loc, I_loc = fed.search_sources(q_list, mask)
+    torch.cuda.synchronize()
+    mask, D_loc, I_loc = mask.cpu().numpy().astype(bool), D_loc.cpu().numpy(), I_loc.cpu().numpy()
+    assert 0.2 < mask.mean() < 0.8
+    for b in range(0, B, 7):
+        feats = router_ref.build_features({m: q_by_model[m][b] for m in models}, _FEB_SOURCES, _FEB_MODEL,
+                                          centroids, _FEB_ID, S, d_max)
+        ref_mask, ref_logits = router_ref.select(sd, feats, 0.5)
+        decided = np.abs(ref_logits) > 1e-5
+        assert np.array_equal(ref_mask[decided], mask[b][decided])
+        for s, n in enumerate(_FEB_SOURCES):
+            Ds, Is = D_loc[b:b + 1, s * k:(s + 1) * k], I_loc[b:b + 1, s * k:(s + 1) * k]
+            if not mask[b, s]:
+                assert (Is == -1).all()
+                continue
+            qv = q_by_model[_FEB_MODEL[n]][b:b + 1]
+            Dr, Ir = flat_ip.search_seq(qv, corpora[n], k)
+            flat_ip.compare_topk(Ds, Is, Dr, Ir, x=qv, xb=corpora[n])
+
+
+def test_routed_large_batch_federation_matches_single_queries(cuda_required):
+    """A routed batch of 300 (large-batch kernels, compaction of the routed queries) must return,
+    query by query, exactly what each query returns alone (swap-AB kernel)."""
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.selftest import build_small_medrag
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation
+    from ragroute_b200.router import MEDRAG_THRESHOLD
+    from ragroute_b200.workloads import make_synthetic_router
+    d, k, B = 768, 32, 300
+    names, sids, corpora, _, _, centroids = build_small_medrag(n_rows=(20000, 30000), d=d)
+    router = make_synthetic_router(names, d, centroids, 11, 0)
+    sources = {}
+    for n in names:
+        ix = IndexFlatIP(d)
+        ix.add(corpora[n])
+        sources[n] = ix
+    fed = Federation(sources, k, router=router, routing="ragroute", threshold=MEDRAG_THRESHOLD)
+    q = torch.from_numpy(syn.queries(B, d, sids, seed=77)).cuda()
+    out = fed.search(q)
+    torch.cuda.synchronize()
+    assert all(sources[n].stats()["exact_rescans"] == 0 for n in names)
+    for b in range(0, B, 23):
+        one = fed.search(q[b:b + 1].contiguous())
+        for key in ("scores", "ids", "source", "mask"):
+            assert torch.equal(one[key][0], out[key][b]), f"query {b}: {key} differs between batch and single"
