@@ -159,3 +159,58 @@ def test_routed_large_batch_federation_matches_single_queries(cuda_required):
         one = fed.search(q[b:b + 1].contiguous())
         for key in ("scores", "ids", "source", "mask"):
             assert torch.equal(one[key][0], out[key][b]), f"query {b}: {key} differs between batch and single"
+
+
+def test_row_shards_merge_to_the_unsharded_result(cuda_required):
+    """Top-k is decomposable: searching W row shards (ids offset by the shard start) and
+    merging their lists equals the unsharded search -- here with all shards on one GPU, which is the
+    per-rank computation of the multi-GPU path without the collective (covered on CPU by the gloo test)."""
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import shard_rows
+    from ragroute_b200.rerank import merge_topk
+    d, k, W = 768, 32, 3
+    xb = syn.corpus_rows(0, 50001, d)
+    for B in (5, 130):
+        q = torch.from_numpy(syn.queries(B, d, [0], seed=B)).cuda()
+        whole = IndexFlatIP(d)
+        whole.add(xb)
+        D0, I0 = whole.search_tensor(q, k)
+        Ds, Is = [], []
+        for r in range(W):
+            lo, hi = shard_rows(len(xb), W, r)
+            ix = IndexFlatIP(d)
+            ix.add(xb[lo:hi])
+            ix.set_id_offset(lo)
+            Dr, Ir = ix.search_tensor(q, k)
+            Ds.append(Dr)
+            Is.append(Ir)
+        Dm, Im, _ = merge_topk(torch.cat(Ds, dim=1).contiguous(), torch.cat(Is, dim=1).contiguous(), k)
+        torch.cuda.synchronize()
+        assert torch.equal(Im, I0) and torch.equal(Dm, D0)
+
+
+def test_micro_batcher_over_a_real_index(cuda_required):
+    """40 concurrent single-query requests (what --parallel 40 sends, run_benchmark.py:90-114) through the
+    collector equal 40 separate index.search calls, and really were batched."""
+    import asyncio
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.collector import MicroBatcher, search_rows
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    d, k = 768, 32
+    xb = syn.corpus_rows(1, 20000, d)
+    ix = IndexFlatIP(d)
+    ix.add(xb)
+    qs = syn.queries(40, d, [1], seed=8)
+
+    async def main():
+        mb = MicroBatcher(lambda embs: search_rows(ix, embs, k), max_batch=64, max_wait_s=0.02)
+        res = await asyncio.gather(*[mb.submit(qs[i].reshape(1, -1)) for i in range(40)])
+        await mb.close()
+        return res, mb
+
+    res, mb = asyncio.run(main())
+    assert mb.batches < 40 and mb.largest_batch > 1
+    for i, (D, I) in enumerate(res):
+        D1, I1 = ix.search(qs[i:i + 1], k)
+        assert np.array_equal(I, I1) and np.array_equal(D, D1)

@@ -297,3 +297,55 @@ def test_gemm_path_mask_chunks_and_default_dispatch(faiss):
     sel = np.nonzero(~off)[0][::37]
     Dr, Ir = oracle.search(q[sel], xb, k)
     oracle.compare_topk(D[sel], I[sel], Dr, Ir, x=q[sel], xb=xb)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE.json sizes.  configs[0] (Textbooks alone, 125 000 x 768, k = 32) is checked against
+# the oracle itself; a multi-million-row corpus is checked through size-independent properties
+# against a float64 torch reference on the device (the CPU oracle would need minutes per query).
+# ---------------------------------------------------------------------------
+def test_config0_textbooks_full_size_vs_oracle(faiss):
+    d, k = syn.MEDRAG_DIM, syn.MEDRAG_K
+    xb = syn.corpus_rows(syn.MEDRAG_SOURCE_TO_ID["textbooks"], syn.MEDRAG_ROWS["textbooks"], d)
+    q = syn.queries(6, d, [2], seed=21)
+    ix = _index(faiss, xb, "auto")
+    D, I = ix.search(q, k)                       # one query at a time is what the reference does; 6 at once here
+    Dr, Ir = oracle.search(q, xb, k)
+    oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
+    D1, I1 = ix.search(q[:1], k)                 # nq = 1, the reference's calling convention (data_source.py:114)
+    assert np.array_equal(I1[0], I[0]) and np.array_equal(D1[0], D[0])
+    assert ix.stats()["exact_rescans"] == 0
+
+
+@pytest.mark.parametrize("nq", [3, 64, 600])
+def test_multi_million_rows_properties(faiss, nq):
+    """3 M x 768 rows generated on the device (seeded): for every kernel family, the returned lists
+    must be sorted, duplicate-free, carry the float64 scores of their rows (<= 1e-5 relative) and no
+    other row of the corpus may beat the k-th score (checked exhaustively in float64 on the GPU)."""
+    from ragroute_b200.workloads import device_rows
+    d, k, n = 768, 32, 3_000_000
+    dev = torch.device("cuda", 0)
+    ix = faiss.IndexFlatIP(d, reserve=n)
+    for _, block in device_rows(0, 0, n, d, dev):
+        ix.add(block)
+    q = torch.from_numpy(syn.queries(nq, d, [0], seed=100 + nq)).cuda()
+    D, I = ix.search_tensor(q, k)
+    torch.cuda.synchronize()
+    assert ix.stats()["exact_rescans"] == 0
+    assert (D[:, :-1] >= D[:, 1:]).all().item(), "scores not descending"
+    assert all(len(set(r)) == k for r in I.cpu().tolist()), "duplicate ids"
+    check = torch.arange(0, nq, max(1, nq // 12), device=dev)           # a dozen queries, exhaustively
+    qd = q[check].double()
+    best = torch.full((len(check), k), -float("inf"), dtype=torch.float64, device=dev)
+    for g0, block in device_rows(0, 0, n, d, dev):
+        s = qd @ block.double().T                                         # [c, rows] float64
+        best = torch.topk(torch.cat([best, s], dim=1), k, dim=1).values
+        sel = (I[check] >= g0) & (I[check] < g0 + block.shape[0])       # float64 scores of the returned rows
+        if sel.any():
+            rows = (I[check] - g0).clamp(0, block.shape[0] - 1)
+            got = torch.gather(s, 1, rows)
+            ref = D[check].double()
+            assert ((got - ref).abs() <= 1e-5 * ref.abs().clamp_min(1e-30))[sel].all().item(), "score mismatch"
+    kth_ref, kth_got = best[:, -1], D[check][:, -1].double()
+    assert ((kth_ref - kth_got).abs() <= 1e-5 * kth_ref.abs()).all().item(), "a better row exists than the returned k-th"
+    assert ((best - D[check].double()).abs() <= 1e-5 * best.abs()).all().item(), "top-k scores differ from float64 truth"
