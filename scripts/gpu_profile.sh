@@ -5,17 +5,17 @@
 # 3) --set full capture of the small-batch scan kernel on the same slice, batch 64
 TAG=${1:-r01}
 mkdir -p gpurun_out
-CMD1="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --sweep 64"
+CMD1="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --sweep 8,64"
 $CMD1 > gpurun_out/${TAG}_plain1.json 2> gpurun_out/${TAG}_plain1.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 600 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD1 > gpurun_out/${TAG}_ncu1.out 2>&1
 echo "launch list exit=$?"
-CMD2="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 1024 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
+CMD2="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 2048 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD2 > gpurun_out/${TAG}_plain2.json 2> gpurun_out/${TAG}_plain2.err &&
 ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
 echo "gemm capture exit=$?"
-CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
+CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 32 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD3 > gpurun_out/${TAG}_plain3.json 2> gpurun_out/${TAG}_plain3.err &&
 ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_scan $CMD3 > gpurun_out/${TAG}_ncu3.out 2>&1
