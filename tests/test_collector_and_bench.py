@@ -102,3 +102,37 @@ def test_bench_gpu_arm_fails_loudly_without_cuda():
                         "--workload", "textbooks"], capture_output=True, text=True, timeout=600, cwd=REPO)
     assert p.returncode != 0 and "no CUDA device" in (p.stderr + p.stdout)
     assert not [l for l in p.stdout.splitlines() if l.strip().startswith("{")], "no number may be printed"
+
+
+def test_router_artifact_files_scaler_and_centroids(tmp_path):
+    """File formats of Router.load_router (router.py:121-151), no GPU involved."""
+    import pickle
+    from sklearn.preprocessing import StandardScaler
+    from ragroute_b200 import artifacts
+    rng = np.random.default_rng(0)
+    scaler = StandardScaler().fit(rng.standard_normal((50, 1540)))
+    p = tmp_path / "preprocessed_data.pkl"
+    with open(p, "wb") as f:
+        pickle.dump(("train", "val", "test", scaler, ["q1"]), f)     # train_medrag_router.py:240-245
+    got = artifacts.load_scaler("medrag", str(p))
+    assert np.array_equal(got.mean_, scaler.mean_) and np.array_equal(got.scale_, scaler.scale_)
+    p2 = tmp_path / "scaler.pkl"
+    with open(p2, "wb") as f:
+        pickle.dump(scaler, f)
+    assert np.array_equal(artifacts.load_scaler("wikipedia", str(p2)).mean_, scaler.mean_)
+    assert artifacts.load_scaler("feb4rag", None) is None
+    # per-corpus stats (medrag) and the clustered list (wikipedia); short centroids are zero padded
+    files = {}
+    for c in ("pubmed", "textbooks"):
+        files[c] = str(tmp_path / f"{c}_stats.json")
+        with open(files[c], "w") as f:
+            json.dump({"centroid": rng.standard_normal(700).tolist(), "n": 3}, f)
+    cen = artifacts.load_centroids("medrag", ["pubmed", "textbooks"], files, 768)
+    assert cen["pubmed"].shape == (768,) and cen["pubmed"].dtype == np.float32 and (cen["pubmed"][700:] == 0).all()
+    cl = str(tmp_path / "cluster_stats.json")
+    with open(cl, "w") as f:
+        json.dump([{"centroid": [float(i)] * 768} for i in range(10)], f)
+    cw = artifacts.load_centroids("wikipedia", ["3", "7"], cl, 768)
+    assert cw["3"][0] == 3.0 and cw["7"][5] == 7.0
+    with pytest.raises(ValueError):
+        artifacts.load_centroids("medrag", ["pubmed"], files, 512)

@@ -106,3 +106,45 @@ def test_merge_topk_vs_oracle_with_ties_and_holes(cuda_required, B, L, k, descen
     rs, ri, rp = rerank_ref.merge_topk(scores, ids, k, descending)
     assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(i.cpu().numpy(), ri)
     assert np.array_equal(p.cpu().numpy(), rp)
+
+
+def test_load_router_from_reference_style_artifacts(cuda_required, tmp_path):
+    """best_model.pth + preprocessed_data.pkl + *_stats.json, laid out as Router.load_router reads them
+    (router.py:106-151), loaded through ragroute_b200.artifacts and checked against the oracle."""
+    import json
+    import pickle
+    import torch
+    from sklearn.preprocessing import StandardScaler
+    from oracle import router_ref
+    from ragroute_b200 import artifacts, synthetic as syn
+    names = ["pubmed", "statpearls", "textbooks", "wikipedia"]
+    d, in_dim = 768, 1540
+    sd = syn.router_state_dict(in_dim, 5)
+    torch.save({k: torch.from_numpy(v) for k, v in sd.items()}, tmp_path / "best_model.pth")
+    rng = np.random.default_rng(2)
+    scaler = StandardScaler().fit(rng.standard_normal((64, in_dim)) * 0.1)
+    with open(tmp_path / "preprocessed_data.pkl", "wb") as f:
+        pickle.dump((None, None, None, scaler, None), f)
+    files, centroids = {}, {}
+    for n in names:
+        centroids[n] = syn.source_mean(syn.MEDRAG_SOURCE_TO_ID[n], d)
+        files[n] = str(tmp_path / f"{n}_stats.json")
+        with open(files[n], "w") as f:
+            json.dump({"centroid": centroids[n].tolist()}, f)
+    model = {n: "ncbi/MedCPT-Query-Encoder" for n in names}
+    router, thr = artifacts.load_router("medrag", names, model, str(tmp_path / "best_model.pth"), files,
+                                        str(tmp_path / "preprocessed_data.pkl"))
+    assert thr == 0.4924 and router.fc1.in_features == in_dim
+    q = syn.queries(9, d, [0, 1, 2, 3], seed=3)
+    thr_logit = router_ref.logit_threshold(thr)
+    for b in range(9):
+        picked = router.select_relevant_sources({"ncbi/MedCPT-Query-Encoder": q[b]}, thr)
+        feats = router_ref.build_features({"m": q[b]}, names, {n: "m" for n in names}, centroids,
+                                          syn.MEDRAG_SOURCE_TO_ID, 4, d)
+        mask, logits = router_ref.select(sd, feats, thr, scaler.mean_, scaler.scale_)
+        sure = np.abs(logits - thr_logit) > 1e-5
+        want = [n for n, m, s in zip(names, mask, sure) if m and s]
+        maybe = [n for n, s in zip(names, sure) if not s]
+        assert all(n in picked for n in want) and all(n in want or n in maybe for n in picked)
+    with pytest.raises(ValueError):
+        artifacts.load_router("bogus", names, model, str(tmp_path / "best_model.pth"), files)
