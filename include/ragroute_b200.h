@@ -80,7 +80,10 @@ int rr_index_reconstruct(rr_index_t* h, int64_t row0, int64_t n, float* out_dev,
 /* ids returned by search are local row numbers + offset (row-sharded corpora) */
 int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
 /* "mode" (RR_MODE_*), "kprime" (candidates rescored per query, default 128),
- * "profile" (1 = record CUDA events around the scan kernels) */
+ * "profile" (1 = record CUDA events around the scan kernels and count the bytes /
+ * flops they cover), "scan_path" (testing: 0 = automatic dispatch, 1 = swap-AB scan in
+ * passes of <= 64 queries, 2 = queries-in-TMEM scan with one CTA per 128-query tile,
+ * 3 = the same on CTA pairs) */
 int rr_index_set_param(rr_index_t* h, const char* name, double value);
 
 /* index.search(x, k) (data_source.py:158,186,203) on device buffers:

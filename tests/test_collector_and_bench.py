@@ -136,3 +136,22 @@ def test_router_artifact_files_scaler_and_centroids(tmp_path):
     assert cw["3"][0] == 3.0 and cw["7"][5] == 7.0
     with pytest.raises(ValueError):
         artifacts.load_centroids("medrag", ["pubmed"], files, 512)
+
+
+def test_wire_format_is_bit_exact_and_smaller_than_json():
+    from ragroute_b200 import wire
+    rng = np.random.default_rng(1)
+    emb = {"ncbi/MedCPT-Query-Encoder": rng.standard_normal(768).astype(np.float32),
+           "e5-large": rng.standard_normal((1, 1024)).astype(np.float32)}
+    frames = wire.pack_message({"query_id": "abc", "data_sources": ["pubmed", "textbooks"]}, emb)
+    h, got = wire.unpack_message(frames)
+    assert h == {"query_id": "abc", "data_sources": ["pubmed", "textbooks"]}
+    for k, v in emb.items():
+        assert got[k].dtype == np.float32 and got[k].shape == v.shape and np.array_equal(got[k], v)
+    as_json = len(json.dumps({k: v.tolist() for k, v in emb.items()}))       # router.py:317-319
+    assert sum(map(len, frames)) < as_json / 3
+    fr = wire.pack_results("abc", 2, "textbooks", np.arange(32), np.linspace(1, 0, 32, dtype=np.float32), 0.001)
+    hh, ids, sc = wire.unpack_results(fr)
+    assert hh["k"] == 32 and ids.tolist() == list(range(32)) and sc.dtype == np.float32 and sc[0] == 1.0
+    with pytest.raises(ValueError):
+        wire.unpack_message([b"nope", b"{}"])
