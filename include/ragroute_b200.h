@@ -58,9 +58,11 @@ int64_t rr_kernel_launches(void);
 
 /* ---------------------------------------------------- B1: flat IP index -- */
 /* Search modes (rr_index_set_param "mode") */
-#define RR_MODE_AUTO 0  /* bf16 tcgen05 scan + fp32-exact rescoring + certificate,
-                           automatic exact rescan of any query whose certificate
-                           fails; results identical to RR_MODE_EXACT            */
+#define RR_MODE_AUTO 0  /* bf16 tcgen05 scan + fp32-exact rescoring + certificate; a
+                           query whose certificate fails is re-done exactly (second
+                           tensor-core pass collecting every row above a provable
+                           threshold, exact scan if that overflows); results
+                           identical to RR_MODE_EXACT                           */
 #define RR_MODE_EXACT 1 /* exact scan only (fp32 rows, fp64 accumulation)       */
 
 /* faiss.IndexFlatIP(d) / faiss.read_index (data_source.py:71).
@@ -115,11 +117,13 @@ int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t nq, int k, 
 typedef struct rr_index_stats {
     int64_t searches;          /* search calls since creation                    */
     int64_t queries;           /* queries since creation                         */
-    int64_t exact_rescans;     /* queries sent to the exact path by certificates */
+    int64_t exact_rescans;     /* queries whose certificate failed (settled exactly by the second,
+                                  thresholded tensor-core pass or, failing that, the exact scan) */
     int64_t scan_launches;     /* bf16 scan kernel launches that were timed      */
     double scan_ms_total;      /* their summed CUDA-event time (profile = 1)     */
     int64_t scan_bytes_total;  /* algorithmic bytes they covered: rows * d_pad*2 */
     int64_t scan_flops_total;  /* algorithmic flops: 2 * routed queries * rows * d_pad */
+    int64_t exact_scans;       /* of exact_rescans: queries that needed the fp64 exact scan */
 } rr_index_stats;
 /* Synchronises the recorded events; resets the timing fields when reset != 0. */
 int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset);

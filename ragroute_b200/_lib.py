@@ -30,7 +30,7 @@ class RRError(RuntimeError):
 class IndexStats(ctypes.Structure):
     _fields_ = [("searches", c_int64), ("queries", c_int64), ("exact_rescans", c_int64),
                 ("scan_launches", c_int64), ("scan_ms_total", c_double), ("scan_bytes_total", c_int64),
-                ("scan_flops_total", c_int64)]
+                ("scan_flops_total", c_int64), ("exact_scans", c_int64)]
 
 
 _P = c_void_p  # device / host pointers are passed as integers

@@ -194,10 +194,10 @@ template <int QSUB>
 __global__ void __launch_bounds__(RR_EXACT_WARPS * 32)
 rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
                      int64_t n_rows, int d_pad, const float* __restrict__ q, int d,
-                     const int* __restrict__ fail_list, const rr_chunk_ctl* __restrict__ ctl,
+                     const int* __restrict__ fail_list, const int* __restrict__ n_fail_ptr,
                      int qsub, float* __restrict__ cand_s,
                      uint32_t* __restrict__ cand_r, int64_t cand_stride) {
-    const int n_fail = ctl->n_fail;
+    const int n_fail = *n_fail_ptr;
     constexpr int M = RR_EXACT_LIST_DEPTH;
     constexpr int W = RR_EXACT_WARPS;
     // sub-batches of failing queries are strided over gridDim.y (a few rows of blocks suffice:
@@ -330,6 +330,7 @@ struct rr_finalize_args {
     rr_chunk_ctl* ctl;
     int* nfail_total;
     int pad_inactive;  // exact-only pipeline: the exact finalize also pads unrouted queries
+    float* theta_q;    // per query: threshold of the second pass when the certificate fails (or NULL)
     const int* cpos;   // large-batch path: candidate row of query qi (compacted); NULL = qi
     int lists_from_ctl;  // large-batch path: the number of lists is ctl->n_lists (decided on the device)
 };
@@ -571,6 +572,7 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     }
 
     bool pass = true;
+    float theta = RR_NEG_INF;  // second-pass threshold if the certificate fails
     if (RESCORE) {
         const float bound = fmaxf(T, t_rest);
         if (bound != RR_NEG_INF) {
@@ -581,8 +583,12 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
             const double qn = (double)a.qnorm[qi];
             const double eps = (3.90625e-3 + 3.814697265625e-6 + (double)a.d_pad * 2.384185791015625e-7) *
                                    qn * xn * 1.00001 + 1e-30;
-            pass = (kp >= a.k) && sel_r[a.k - 1] != RR_NO_ROW &&
-                   ((double)sel_s[a.k - 1] > (double)bound + eps);
+            const bool have_k = (kp >= a.k) && sel_r[a.k - 1] != RR_NO_ROW;
+            pass = have_k && ((double)sel_s[a.k - 1] > (double)bound + eps);
+            // L = the k-th exact score among the candidates is a lower bound of the true k-th score, and a
+            // row with exact score >= L has bf16 score >= L - eps: the second pass collects every row
+            // whose bf16 score is > theta = the largest float below L - eps
+            if (!pass && have_k) theta = nextafterf(__double2float_rd((double)sel_s[a.k - 1] - eps), RR_NEG_INF);
         }
     }
     if (pass) {
@@ -593,9 +599,160 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
         }
     } else if (tid == 0) {
         a.fail_flags[qi] = 1;
+        if (RESCORE && a.theta_q) a.theta_q[qi] = theta;
         a.fail_list[atomicAdd(&a.ctl->n_fail, 1)] = qi;
         atomicAdd(a.nfail_total, 1);
     }
+}
+
+// ---- second pass ("collect") for the queries whose certificate failed --------------------------
+// Gather their bf16 rows (in fail_list order) into the second query buffer, hand their thresholds to
+// the scan, zero their row counters.  grid = rows of the second buffer, 128 threads.
+__global__ void __launch_bounds__(128)
+rr_prep_collect_kernel(const uint16_t* __restrict__ qbf16, const int* __restrict__ cpos, int d_pad,
+                       const int* __restrict__ fail_list, const float* __restrict__ theta_q,
+                       const rr_chunk_ctl* __restrict__ ctl, uint16_t* __restrict__ qbf2, float* __restrict__ theta2,
+                       int* __restrict__ col_cnt, rr_chunk_ctl* ctl2, int nq) {
+    const int i = blockIdx.x;
+    const int n_fail = ctl->n_fail;
+    if (i == 0 && threadIdx.x == 0) {
+        ctl2->n_active = n_fail;
+        ctl2->any_active = n_fail > 0;
+    }
+    if (n_fail == 0) return;  // nothing failed: the scan that follows exits at once, leave the buffer alone
+    uint4* out = reinterpret_cast<uint4*>(qbf2 + (int64_t)i * d_pad);
+    if (i < n_fail) {
+        const int qi = fail_list[i];
+        const uint4* in = reinterpret_cast<const uint4*>(qbf16 + (int64_t)(cpos ? cpos[qi] : qi) * d_pad);
+        for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = in[e];
+        if (threadIdx.x == 0) theta2[i] = theta_q[qi];
+    } else {
+        for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = make_uint4(0, 0, 0, 0);
+        if (threadIdx.x == 0) theta2[i] = __builtin_huge_valf();
+    }
+    if (threadIdx.x == 0 && i < nq) col_cnt[i] = 0;
+}
+
+constexpr int RR_COLLECT_CAP = 2048;  // rows a failing query may collect before it goes to the exact scan
+
+struct rr_collect_fin_args {
+    const uint32_t* col_rows;  // [i][RR_COLLECT_CAP], i = position in fail_list
+    const int* col_cnt;
+    const int* fail_list;
+    rr_chunk_ctl* ctl;
+    int* fail2_list;
+    uint8_t* fail_flags;
+    int* n_exact_total;
+    int k;
+    const float* q;
+    const uint16_t* hi;
+    const uint16_t* lo;
+    int d;
+    int d_pad;
+    int64_t id_offset;
+    float* D;
+    int64_t* I;
+    int64_t out_stride;
+};
+
+// One block per failing query: every row that can possibly belong to its top-k was collected; score
+// them exactly (fp32 rows rebuilt from the planes, fp64 accumulate) and keep the k best by
+// (score desc, row asc) -- no certificate needed.  A query whose list overflowed goes to the exact scan.
+__global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_collect_kernel(rr_collect_fin_args a) {
+    const int i = blockIdx.x;
+    if (i >= a.ctl->n_fail) return;
+    const int qi = a.fail_list[i];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int cnt = a.col_cnt[i];
+    if (cnt > RR_COLLECT_CAP) {  // too many near-ties: exact scan
+        if (tid == 0) {
+            a.fail2_list[atomicAdd(&a.ctl->n_fail2, 1)] = qi;
+            atomicAdd(a.n_exact_total, 1);
+        }
+        return;
+    }
+    __shared__ float s_s[RR_COLLECT_CAP];
+    __shared__ uint32_t s_r[RR_COLLECT_CAP];
+    extern __shared__ __align__(16) float q_sm[];  // [d_pad]
+    const float* qr = a.q + (int64_t)qi * a.d;
+    for (int e = tid; e < a.d_pad; e += blockDim.x) q_sm[e] = (e < a.d) ? qr[e] : 0.f;
+    int n_pad = 32;
+    while (n_pad < cnt) n_pad <<= 1;
+    for (int j = tid; j < n_pad; j += blockDim.x) {
+        s_r[j] = (j < cnt) ? a.col_rows[(int64_t)i * RR_COLLECT_CAP + j] : RR_NO_ROW;
+        s_s[j] = RR_NEG_INF;
+    }
+    __syncthreads();
+    constexpr int RB = 4;
+    constexpr int NW = RR_FIN_THREADS / 32;
+    for (int i0 = w * RB; i0 < cnt; i0 += NW * RB) {
+        double acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+        for (int e0 = lane * 8; e0 < a.d_pad; e0 += 256) {
+            uint4 hv[RB], lv[RB];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int64_t row = s_r[min(i0 + r, cnt - 1)];
+                hv[r] = __ldg(reinterpret_cast<const uint4*>(a.hi + row * a.d_pad) + (e0 >> 3));
+                lv[r] = __ldg(reinterpret_cast<const uint4*>(a.lo + row * a.d_pad) + (e0 >> 3));
+            }
+            const float4 qa = *reinterpret_cast<const float4*>(q_sm + e0);
+            const float4 qb = *reinterpret_cast<const float4*>(q_sm + e0 + 4);
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                double s_ = acc[r];
+                float2 t;
+                t = rr_join_f32x2(hv[r].x, lv[r].x);
+                s_ = fma((double)t.x, (double)qa.x, s_);
+                s_ = fma((double)t.y, (double)qa.y, s_);
+                t = rr_join_f32x2(hv[r].y, lv[r].y);
+                s_ = fma((double)t.x, (double)qa.z, s_);
+                s_ = fma((double)t.y, (double)qa.w, s_);
+                t = rr_join_f32x2(hv[r].z, lv[r].z);
+                s_ = fma((double)t.x, (double)qb.x, s_);
+                s_ = fma((double)t.y, (double)qb.y, s_);
+                t = rr_join_f32x2(hv[r].w, lv[r].w);
+                s_ = fma((double)t.x, (double)qb.z, s_);
+                s_ = fma((double)t.y, (double)qb.w, s_);
+                acc[r] = s_;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RB; ++r) {
+            const double tot = rr_warp_sum(acc[r]);
+            if (lane == 0 && i0 + r < cnt) s_s[i0 + r] = (float)tot;
+        }
+    }
+    __syncthreads();
+    for (int ksz = 2; ksz <= n_pad; ksz <<= 1) {
+        for (int j = ksz >> 1; j > 0; j >>= 1) {
+            for (int x = tid; x < n_pad; x += blockDim.x) {
+                const int y = x ^ j;
+                if (y > x) {
+                    const bool first_low = (x & ksz) == 0;
+                    const float s1 = s_s[x], s2 = s_s[y];
+                    const uint32_t r1 = s_r[x], r2 = s_r[y];
+                    const bool swap = first_low ? rr_before(s2, r2, s1, r1) : rr_before(s1, r1, s2, r2);
+                    if (swap) {
+                        s_s[x] = s2;
+                        s_r[x] = r2;
+                        s_s[y] = s1;
+                        s_r[y] = r1;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    float* Dq = a.D + (int64_t)qi * a.out_stride;
+    int64_t* Iq = a.I + (int64_t)qi * a.out_stride;
+    for (int x = tid; x < a.k; x += blockDim.x) {
+        const bool ok = (x < cnt) && s_r[x] != RR_NO_ROW;
+        Dq[x] = ok ? s_s[x] : -3.402823466e+38f;
+        Iq[x] = ok ? (int64_t)s_r[x] + a.id_offset : (int64_t)-1;
+    }
+    if (tid == 0) a.fail_flags[qi] = 0;  // settled: the exact finalize skips it
 }
 
 // ------------------------------------------------------------------- host ---
@@ -824,6 +981,7 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
     unsigned long long ctr[4] = {0, 0, 0, 0};  // [0] low int = certificate failures, [1] bytes, [2] flops
     RR_CUDA_CHECK(cudaMemcpy(ctr, h->d_nfail_total, 32, cudaMemcpyDeviceToHost));
     h->stats.exact_rescans = (int)(ctr[0] & 0xFFFFFFFFull);
+    h->stats.exact_scans = (int)(ctr[0] >> 32);
     h->stats.scan_bytes_total = (int64_t)ctr[1];
     h->stats.scan_flops_total = (int64_t)ctr[2];
     *out = h->stats;
@@ -887,6 +1045,17 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     const size_t o_ff = carve((size_t)nq_pad);
     const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
     const size_t o_cp = carve((size_t)nq_pad * sizeof(int));
+    // second pass (queries whose certificate failed), only when the first pass was a tensor-core scan
+    const bool use_pass2 = (use_tc || use_gemm) && rr_gemm_scan_supported(h);
+    const int cg2 = rr_gemm_cta_group(h, nq);
+    const int nq_pad2 = use_pass2 ? (int)rr_align_up((size_t)nq, (size_t)RR_GEMM_QTILE * cg2) : 0;
+    const size_t o_ctl2 = carve(sizeof(rr_chunk_ctl));
+    const size_t o_qb2 = carve((size_t)nq_pad2 * h->d_pad * sizeof(uint16_t));
+    const size_t o_thq = carve((size_t)nq_pad * sizeof(float));
+    const size_t o_th2 = carve((size_t)nq_pad2 * sizeof(float));
+    const size_t o_cc = carve((size_t)nq_pad2 * sizeof(int));
+    const size_t o_f2 = carve((size_t)nq_pad * sizeof(int));
+    const size_t o_cr2 = carve(use_pass2 ? (size_t)nq * RR_COLLECT_CAP * sizeof(uint32_t) : 0);
     const size_t o_cs = carve((size_t)nq * cand_stride * sizeof(float));
     const size_t o_cr = carve((size_t)nq * cand_stride * sizeof(uint32_t));
     if (off > h->scratch_bytes) {
@@ -902,6 +1071,13 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     uint8_t* fail_flags = (uint8_t*)(base + o_ff);
     int* fail_list = (int*)(base + o_fl);
     int* cpos = (int*)(base + o_cp);
+    rr_chunk_ctl* ctl2 = (rr_chunk_ctl*)(base + o_ctl2);
+    uint16_t* qbf2 = (uint16_t*)(base + o_qb2);
+    float* theta_q = (float*)(base + o_thq);
+    float* theta2 = (float*)(base + o_th2);
+    int* col_cnt = (int*)(base + o_cc);
+    int* fail2_list = (int*)(base + o_f2);
+    uint32_t* col_rows = (uint32_t*)(base + o_cr2);
     float* cand_s = (float*)(base + o_cs);
     uint32_t* cand_r = (uint32_t*)(base + o_cr);
 
@@ -942,6 +1118,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     fa.pad_inactive = (use_tc || use_gemm) ? 0 : 1;
     fa.cpos = nullptr;
     fa.lists_from_ctl = 0;
+    fa.theta_q = use_pass2 ? theta_q : nullptr;
 
     if (use_gemm) {
         // one launch covers the whole chunk: queries stationary in TMEM, corpus read once
@@ -952,7 +1129,8 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
             RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
         }
         int rc = rr_gemm_scan_launch(h, qbf, nq, gemm_cg, ctl, cand_s, cand_r, cand_stride,
-                                     prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr, stream);
+                                     prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr, nullptr,
+                                     stream);
         if (rc != RR_OK) return rc;
         rr_count_launch(1);
         if (prof) {
@@ -997,7 +1175,48 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
         rr_count_launch(1);
     }
 
-    // exact path over fail_list (everything when !use_tc); launches exit at once when empty
+    // second pass over the queries whose certificate failed: the tensor-core scan again, this time
+    // reporting every row above a per-query threshold that provably keeps the whole exact top-k; then
+    // exact scores of those rows.  All three launches exit at once when nothing failed.
+    const int* exact_list = fail_list;
+    const int* exact_count = &ctl->n_fail;
+    if (use_pass2) {
+        rr_prep_collect_kernel<<<nq_pad2, 128, 0, stream>>>(qbf, use_gemm ? cpos : nullptr, h->d_pad, fail_list, theta_q,
+                                                            ctl, qbf2, theta2, col_cnt, ctl2, nq);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_collect_args ca;
+        ca.theta = theta2;
+        ca.rows = col_rows;
+        ca.cnt = col_cnt;
+        ca.cap = RR_COLLECT_CAP;
+        int rc = rr_gemm_scan_launch(h, qbf2, nq, cg2, ctl2, nullptr, nullptr, 0, nullptr, &ca, stream);
+        if (rc != RR_OK) return rc;
+        rr_collect_fin_args cf;
+        cf.col_rows = col_rows;
+        cf.col_cnt = col_cnt;
+        cf.fail_list = fail_list;
+        cf.ctl = ctl;
+        cf.fail2_list = fail2_list;
+        cf.fail_flags = fail_flags;
+        cf.n_exact_total = h->d_nfail_total + 1;
+        cf.k = k;
+        cf.q = q_dev;
+        cf.hi = h->hi;
+        cf.lo = h->lo;
+        cf.d = h->d;
+        cf.d_pad = h->d_pad;
+        cf.id_offset = h->id_offset;
+        cf.D = D_dev;
+        cf.I = I_dev;
+        cf.out_stride = out_stride;
+        rr_finalize_collect_kernel<<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(cf);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(3);
+        exact_list = fail2_list;
+        exact_count = &ctl->n_fail2;
+    }
+
+    // exact path over what is left (everything when there was no tensor-core pass); launches exit at once when empty
     int qsub = RR_EXACT_MAX_QSUB;
     while (qsub > 1 && (size_t)qsub * h->d_pad * sizeof(float) > (96u << 10)) qsub >>= 1;
     const size_t ex_smem = (size_t)qsub * h->d_pad * sizeof(float) +
@@ -1014,7 +1233,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
         // one launch covers every sub-batch; blocks beyond the failing queries exit at once
         const dim3 grid((unsigned)g_exact, (unsigned)std::min(4, (nq + qsub - 1) / qsub));
         rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
-            h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, fail_list, ctl, qsub, cand_s, cand_r, cand_stride);
+            h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, exact_list, exact_count, qsub, cand_s, cand_r, cand_stride);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
     }

@@ -70,6 +70,16 @@ struct rr_chunk_ctl {
     int any_active;  // at least one query is routed to this source
     int n_active;    // large-batch path: routed queries (they are compacted to rows [0, n_active))
     int n_lists;     // large-batch path: candidate lists per query the scan produced
+    int n_fail2;     // queries the second pass could not settle (row list overflow): exact scan
+    int pad_[3];
+};
+// second pass ("collect"): per-query fixed thresholds in, per-query row lists out (all device memory,
+// indexed by the compact query order of that pass)
+struct rr_collect_args {
+    const float* theta;  // rows with bf16 score > theta[q] are reported
+    uint32_t* rows;      // [q][cap]
+    int* cnt;            // [q], zeroed by the caller; may end above cap (overflow)
+    int cap;
 };
 // profiling counters handed to the scan kernels (or NULL): [0] bytes streamed, [1] flops scored
 struct rr_scan_counters {
@@ -106,4 +116,4 @@ int rr_gemm_scan_max_lists(const rr_index* h);
 // for which qbf16 holds ceil(nq / 256) * 256 rows.
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
                         float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
-                        cudaStream_t stream);
+                        const rr_collect_args* collect, cudaStream_t stream);

@@ -68,6 +68,12 @@ struct GemmParams {
     const uint16_t* qbf16;    // [ceil(nq / 128) * 128][d_pad] bf16: routed queries first, then zero rows
     rr_chunk_ctl* ctl;        // n_active (in), n_lists (out)
     rr_scan_counters* counters;
+    // COLLECT mode (second pass for queries whose certificate failed): fixed thresholds, every row that
+    // beats its query's threshold is appended to that query's row list
+    const float* theta;     // [compact query] rows with score > theta are collected
+    uint32_t* col_rows;     // [compact query][col_cap]
+    int* col_cnt;           // [compact query] (may exceed col_cap: overflow, the caller falls back)
+    int col_cap;
     float* cand_s;  // [compact query][slice][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
@@ -79,6 +85,14 @@ struct GemmParams {
 // Drain the pending queues of a warp: round i inserts the i-th pending survivor of every thread
 // that has one.  Out of line: it runs for a fraction of the tiles.
 constexpr int kPend = 16;  // pending slots per thread
+
+// COLLECT mode: the pending survivors go to the query's global row list (thresholds are fixed).
+__device__ __noinline__ void epi_collect(int cnt, int qg, const GemmParams& p, const uint32_t* pr, int t) {
+    for (int i = 0; i < cnt; ++i) {
+        const int pos = atomicAdd(p.col_cnt + qg, 1);
+        if (pos < p.col_cap) p.col_rows[(int64_t)qg * p.col_cap + pos] = pr[i * kQTile + t];
+    }
+}
 
 __device__ __noinline__ void epi_drain(int cnt, float& thr, int& pos, float* ls, uint32_t* lr, const float* ps,
                                        const uint32_t* pr, int t) {
@@ -115,7 +129,9 @@ static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA b
 //         CTA, each in its own TMEM) against the same 128-row corpus tiles, of which each CTA
 //         streams only 64 rows -- per SM half the L2->smem traffic and half the shared-memory
 //         operand reads per flop, which is what bounds CG = 1.
-template <int CG>
+// COLLECT = false: per-query top-32 lists (first pass).  COLLECT = true: fixed per-query thresholds, every
+// row above them is reported (second pass for the queries whose certificate failed).
+template <int CG, bool COLLECT>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                     const GemmParams p) {
@@ -131,7 +147,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     const int qt = (unit % nqt) * CG + (int)rank;  // this CTA's 128-query tile
     const int slice = unit / nqt;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        p.ctl->n_lists = n_slices;
+        if (!COLLECT) p.ctl->n_lists = n_slices;
         if (p.counters) {
             atomicAdd(&p.counters->bytes, (unsigned long long)p.n_rows * (unsigned long long)p.num_kc * 128ull);
             atomicAdd(&p.counters->flops,
@@ -361,7 +377,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             ls[e * kQTile + t] = RR_NEG_INF;
             lr[e * kQTile + t] = RR_NO_ROW;
         }
-        float thr = (qg < n_active) ? RR_NEG_INF : __builtin_huge_valf();
+        float thr = (qg < n_active) ? (COLLECT ? p.theta[qg] : RR_NEG_INF) : __builtin_huge_valf();
         int pos = 0;  // slot of the list's minimum (an empty slot while there is one)
         int cnt = 0;  // pending survivors
 
@@ -428,21 +444,23 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         }
                         // a group adds at most 8 entries per thread: drain before the queue could overflow
                         if (__any_sync(RR_FULL, cnt > kPend - 8)) {
-                            epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                            if (COLLECT) epi_collect(cnt, qg, p, pr, t);
+                            else epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
                             cnt = 0;
                         }
                     }
                 }
                 // one drain per tile serves every query of the warp that had survivors
                 if (__any_sync(RR_FULL, cnt > 0)) {
-                    epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                    if (COLLECT) epi_collect(cnt, qg, p, pr, t);
+                    else epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
                     cnt = 0;
                 }
             }
         }
         // publish [compact query][list = slice][kDepth]: the list's minimum goes to the LAST slot (the tail
         // that bounds every dropped row; an empty slot there = nothing was dropped), the rest unsorted
-        if (qg < n_active) {
+        if (!COLLECT && qg < n_active) {
             const int64_t o = (int64_t)qg * p.cand_stride + (int64_t)slice * kDepth;
             int w = 0;
             for (int e = 0; e < kDepth; ++e) {
@@ -475,7 +493,7 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
-template <int CG>
+template <int CG, bool COLLECT>
 static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, cudaStream_t stream) {
     const size_t stage_b = (size_t)kStageBytes / CG;
     const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
@@ -484,7 +502,7 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     const size_t smem = fixed + (size_t)p.stages * stage_b;
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
         attr_done[h->device & 63] = true;
     }
@@ -501,13 +519,13 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG>, tx, tq, p));
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT>, tx, tq, p));
     return RR_OK;
 }
 
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
                         float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
-                        cudaStream_t stream) {
+                        const rr_collect_args* collect, cudaStream_t stream) {
     RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
     RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
     RR_REQUIRE(cta_group == 1 || cta_group == 2, "rr_gemm_scan_launch: cta_group must be 1 or 2");
@@ -542,12 +560,20 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
     p.cand_s = cand_s;
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
-    RR_REQUIRE((int64_t)h->sm_count * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
+    p.theta = collect ? collect->theta : nullptr;
+    p.col_rows = collect ? collect->rows : nullptr;
+    p.col_cnt = collect ? collect->cnt : nullptr;
+    p.col_cap = collect ? collect->cap : 0;
+    RR_REQUIRE(collect || (int64_t)h->sm_count * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
     // the tail of each query tile is fetched by TMA from the bf16 query buffer
     const int q_align = kQTile * cta_group;
     const int nq_rows = (nq + q_align - 1) / q_align * q_align;
     alignas(64) CUtensorMap tq;
     int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, nq_rows, h->d_pad, kQTile);
     if (rc != RR_OK) return rc;
-    return cta_group == 2 ? launch_cg<2>(h, h->tmap_hi64, tq, p, stream) : launch_cg<1>(h, h->tmap_hi, tq, p, stream);
+    if (collect)
+        return cta_group == 2 ? launch_cg<2, true>(h, h->tmap_hi64, tq, p, stream)
+                              : launch_cg<1, true>(h, h->tmap_hi, tq, p, stream);
+    return cta_group == 2 ? launch_cg<2, false>(h, h->tmap_hi64, tq, p, stream)
+                          : launch_cg<1, false>(h, h->tmap_hi, tq, p, stream);
 }

@@ -11,7 +11,7 @@ run() { # name, pytest args...
 run router_rerank tests/test_gpu_router_rerank.py
 run index_exact tests/test_gpu_index.py -k "exact or reconstruct or normalize or errors or offset"
 run index_tcscan tests/test_gpu_index.py -k "tc_scan_candidates"
-run index_auto tests/test_gpu_index.py -k "not exact and not tc_scan_candidates and not reconstruct and not normalize and not errors and not offset and not gemm and not config0 and not multi_million"
+run index_auto tests/test_gpu_index.py -k "not exact and not tc_scan_candidates and not reconstruct and not normalize and not errors and not offset and not gemm and not config0 and not multi_million and not near_duplicate"
 run index_gemm tests/test_gpu_index.py -k "gemm"
-run index_sizes tests/test_gpu_index.py -k "config0 or multi_million"
+run index_sizes tests/test_gpu_index.py -k "config0 or multi_million or near_duplicate"
 run federation tests/test_gpu_federation.py

@@ -142,7 +142,9 @@ def test_adversarial_near_ties_fall_back_to_exact(faiss):
     D, I = ix.search(q, k)
     Dr, Ir = oracle.search_seq(q, xb, k)
     oracle.compare_topk(D, I, Dr, Ir, x=q, xb=xb)
-    assert ix.stats()["exact_rescans"] >= 1, "the certificate should have rejected the bf16 ranking"
+    st = ix.stats()
+    assert st["exact_rescans"] >= 1, "the certificate should have rejected the bf16 ranking"
+    assert st["exact_scans"] >= 1, "4096 rows inside one bf16 ulp overflow the second pass: exact scan expected"
     # the library's own contract: fp64-accumulated score rounded to fp32, ties by lower id
     t32 = (xb.astype(np.float64) @ q[0].astype(np.float64)).astype(np.float32)
     want = np.lexsort((np.arange(n), -t32.astype(np.float64)))[:k]
@@ -349,3 +351,30 @@ def test_multi_million_rows_properties(faiss, nq):
     kth_ref, kth_got = best[:, -1], D[check][:, -1].double()
     assert ((kth_ref - kth_got).abs() <= 1e-5 * kth_ref.abs()).all().item(), "a better row exists than the returned k-th"
     assert ((best - D[check].double()).abs() <= 1e-5 * best.abs()).all().item(), "top-k scores differ from float64 truth"
+
+
+@pytest.mark.parametrize("nq,path", [(1, 0), (40, 0), (64, 0), (300, 0), (300, 2), (1500, 0)])
+def test_near_duplicate_documents_are_settled_by_the_second_pass(faiss, nq, path):
+    """Documents stored as runs of ~100 near-duplicate chunks: the whole top-32 of a query falls inside one
+    candidate list's territory, so the first-pass certificate MUST fail; the thresholded second tensor-core
+    pass collects every row that can matter and the result is bit-identical to the exact scan, without it."""
+    d, k, docs, per = 768, 32, 300, 100
+    rng = np.random.default_rng(11)
+    centers = (rng.standard_normal((docs, d)) / np.sqrt(d) + 0.02).astype(np.float32)
+    xb = (np.repeat(centers, per, axis=0) +
+          0.03 * rng.standard_normal((docs * per, d)).astype(np.float32) / np.float32(np.sqrt(d))).astype(np.float32)
+    pick = rng.integers(0, docs, size=nq)
+    q = (centers[pick] + 0.05 * rng.standard_normal((nq, d)).astype(np.float32) / np.float32(np.sqrt(d))).astype(np.float32)
+    ix = _index(faiss, xb, "auto")
+    if path:
+        ix.set_param("scan_path", path)
+    D, I = ix.search(q, k)
+    st = ix.stats()
+    assert st["exact_rescans"] > 0.5 * nq, f"expected certificate failures on near-duplicate runs: {st}"
+    assert st["exact_scans"] == 0, f"the second pass should have settled every query: {st}"
+    De, Ie = _index(faiss, xb, "exact").search(q, k)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De), "second pass and exact scan must agree bit for bit"
+    assert ((I // per) == pick[:, None]).mean() > 0.95     # the top-32 really are the query's own document
+    sel = np.arange(0, nq, max(1, nq // 5))
+    Dr, Ir = oracle.search(q[sel], xb, k)
+    oracle.compare_topk(D[sel], I[sel], Dr, Ir, x=q[sel], xb=xb)
