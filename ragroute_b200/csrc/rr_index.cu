@@ -870,7 +870,8 @@ extern "C" int rr_index_add_f32(rr_index_t* h, const float* x, int64_t n, int x_
     RR_REQUIRE(n >= 0, "rr_index_add_f32: negative n");
     if (n == 0) return RR_OK;
     RR_REQUIRE(x != nullptr, "rr_index_add_f32: x is NULL");
-    RR_REQUIRE(h->n + n <= 0xFFFFFFF0ll, "rr_index_add_f32: more than 2^32 rows in one shard");
+    // local row ids are u32 in the candidate lists and int32 TMA coordinates in the scan kernels
+    RR_REQUIRE(h->n + n <= 0x7FFFFF00ll, "rr_index_add_f32: more than 2^31 rows in one shard");
     rr_device_guard g(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
     if (h->n + n > h->cap) {
