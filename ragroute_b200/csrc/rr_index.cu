@@ -5,15 +5,24 @@
 // the same footprint as FAISS' fp32 rows, of which a scan streams only 2.
 //
 // Search pipeline for a chunk of queries (all on one stream, no host sync):
-//   prep      fp32 queries -> bf16 tile (+ L2 norms for the certificate)
-//   tc scan   rr_scan_tc.cu: TMA + tcgen05 scores, per-warp top-16 lists
+//   compact   (large batch) routed queries to the front, so unrouted pairs cost nothing
+//   prep      fp32 queries -> bf16 rows (+ L2 norms for the certificate)
+//   scan      <= 48 queries: rr_scan_tc.cu (swap-AB, per-warp top-16 lists);
+//             more: rr_scan_gemm.cu (queries stationary in TMEM, per-query top-32 lists,
+//             CTA pairs above 256 queries)
 //   finalize  per query: radix-select the kprime best bf16 candidates, rescore
 //             them exactly (fp32 rows rebuilt from the planes, fp64 accumulate),
 //             sort, and CERTIFY: every row that is not a candidate has bf16 score
 //             <= bound, hence exact score <= bound + eps(|q|, max|x|, d); the
 //             result is accepted iff the k-th exact score is above that.
-//   exact     queries whose certificate failed are rescanned with the exact
-//             kernel (lists of depth 32 >= k, so unconditional) and finalized.
+//   collect   queries whose certificate failed go through the tensor-core scan again
+//             with a fixed threshold (k-th candidate score - eps) that provably keeps
+//             the whole top-k; the rows above it are scored exactly -> exact result.
+//   exact     queries whose row list overflowed in `collect` (or every query in
+//             RR_MODE_EXACT / for dimensions the tensor-core kernels do not take) are
+//             scanned with the exact kernel (fp64 accumulate, lists of depth 32 >= k).
+// Every stage after `finalize` is launched unconditionally and exits at once when no
+// query needs it.
 #include <math.h>
 #include <string.h>
 
