@@ -437,7 +437,9 @@ def gpu_main(args, rows, workload):
         line = {
             "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_run["ms_total"] / args.steps, "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "bf16 scan + f32-exact rescoring (f64 accumulate)", "data": "synthetic",
+            "vs_baseline": None, "dtype": "bf16",
+            "dtype_detail": "bf16 tensor-core scan selects candidates; returned scores are fp32-exact (fp32 rows, fp64 accumulate)",
+            "data": "synthetic",
             "config": {"workload": workload, "rows": rows, "rows_rank0": local_rows, "dim": D, "k": K, "batch": B,
                        "routing": args.routing, "mask_density": mask_density,
                        "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
