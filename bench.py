@@ -286,6 +286,9 @@ def gpu_main(args, rows, workload):
         ix.set_param("profile", 1)
         if args.scan_path:
             ix.set_param("scan_path", args.scan_path)
+        for kv in args.index_param:
+            name, val = kv.split("=")
+            ix.set_param(name, float(val))
 
     def barrier():
         if world > 1:
@@ -417,12 +420,12 @@ def gpu_main(args, rows, workload):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.time()
-        cqps, cms, info = run_cpu_reference(rows, B, steps=2, warmup=1,
+        cqps, cms, info = run_cpu_reference(rows, B, steps=4, warmup=1,
                                             sample_rows_total=cpu_sample_rows(args.cpu_sample_rows, B))
         cpu_baseline = {
             "value": cqps, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
             "sample": (f"{sum(info['rows_sampled'].values())} of {sum(rows.values())} rows "
-                       f"({info['row_fraction']:.4%}), batch {B}, 2 timed steps, routed pairs only "
+                       f"({info['row_fraction']:.4%}), batch {B}, 4 timed steps, routed pairs only "
                        f"(mask density {info['mask_density']:.2f}), FAISS-restated sequential scan, OpenMP over "
                        f"queries; queries/s scaled linearly in rows; {time.time() - t0:.1f}s wall"),
         }
@@ -484,8 +487,10 @@ def main():
     ap.add_argument("--rows-scale", type=float, default=1.0, help="scale every source's row count (debug)")
     ap.add_argument("--sweep", default="1,8,64,256", help="comma separated extra batch sizes ('' = none)")
     ap.add_argument("--sweep-ms-budget", type=float, default=1500.0)
-    ap.add_argument("--cpu-sample-rows", type=int, default=600_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_500_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--index-param", action="append", default=[], metavar="NAME=VALUE",
+                    help="rr_index_set_param on every source (experiments), e.g. gemm_tmem_all=0")
     ap.add_argument("--scan-path", type=int, default=0,
                     help="debug: force a scan kernel (1 = 64-query passes, 2 = large-batch, 3 = large-batch CTA pairs)")
     args = ap.parse_args()

@@ -85,7 +85,8 @@ int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
  * "profile" (1 = record CUDA events around the scan kernels and count the bytes /
  * flops they cover), "scan_path" (testing: 0 = automatic dispatch, 1 = swap-AB scan in
  * passes of <= 64 queries, 2 = queries-in-TMEM scan with one CTA per 128-query tile,
- * 3 = the same on CTA pairs) */
+ * 3 = the same on CTA pairs), "gemm_tmem_all" (testing: 0 = keep the two-accumulator layout of the
+ * queries-in-TMEM scan even for <= 128 queries) */
 int rr_index_set_param(rr_index_t* h, const char* name, double value);
 
 /* index.search(x, k) (data_source.py:158,186,203) on device buffers:
@@ -108,6 +109,20 @@ int rr_index_search_masked(rr_index_t* h, const float* q_dev, int64_t nq, int k,
 int rr_index_search_ex(rr_index_t* h, const float* q_dev, int64_t nq, int k, const uint8_t* mask_dev,
                        int64_t mask_stride, float* D_dev, int64_t* I_dev, int64_t out_stride,
                        void* stream);
+/* One routed step over n_sources indexes at once: the fan-out of one query batch to the selected
+ * data sources (ragroute/http_server.py:200-209) followed by each source's index.search
+ * (data_source.py:186), with the per-source lists written side by side for the merge
+ * (http_server.py:280-289).  Same results as n_sources rr_index_search_ex calls; the scans stay one
+ * launch per source, every other stage runs as one launch for all sources (fixed cost per step
+ * instead of per source).
+ *   idx [n_sources] handles on ONE device, each listed once;
+ *   q_dev [n_sources] device pointers, q_dev[s] = [nq, dim(idx[s])] fp32 (sources sharing an
+ *   encoder pass the same pointer);
+ *   mask_dev [nq, mask_stride] uint8 or NULL (all routed): column s gates source s;
+ *   D_dev / I_dev [nq, out_stride]: source s writes columns [s*k, (s+1)*k); out_stride 0 = n_sources*k. */
+int rr_federation_search(rr_index_t* const* idx, int n_sources, const float* const* q_dev, int64_t nq,
+                         int k, const uint8_t* mask_dev, int64_t mask_stride, float* D_dev,
+                         int64_t* I_dev, int64_t out_stride, void* stream);
 /* Host-buffer convenience used by the faiss-shaped Python object: copies q in,
  * searches, copies D / I out and synchronises (this is the reference's calling
  * convention: numpy in, numpy out). */
@@ -180,6 +195,19 @@ int rr_router_select(rr_router_t* h, const float* q_dev, int64_t B, float prob_t
 #define RR_MERGE_MAX_L 4096
 int rr_merge_topk(const float* s_dev, const int64_t* id_dev, int64_t B, int L, int k,
                   int descending, float* os_dev, int64_t* oid_dev, int32_t* opos_dev, void* stream);
+
+/* The same merge over lists that arrive as n_seg separate [B, seg_len] blocks -- the all-gathered
+ * per-rank lists of a row-sharded federation (one block per rank, seg_stride_* elements apart), read in
+ * place -- with the winner's origin decoded on the device.  Entry j of block g has input position
+ * g * seg_len + j, so the result equals rr_merge_topk over the concatenation [B, n_seg * seg_len].
+ *   list_len > 0: every block holds seg_len / list_len per-source lists of list_len entries (what
+ *   rr_federation_search writes); then osrc [B, k] = list (source) index inside the block and
+ *   orank [B, k] = block (rank) index of each winner, -1 in unused slots.  Any of opos / osrc / orank
+ *   may be NULL.  n_seg * seg_len <= RR_MERGE_MAX_L. */
+int rr_merge_topk_segments(const float* s_dev, const int64_t* id_dev, int64_t B, int n_seg, int seg_len,
+                           int64_t seg_stride_s, int64_t seg_stride_id, int k, int descending,
+                           int list_len, float* os_dev, int64_t* oid_dev, int32_t* opos_dev,
+                           int32_t* osrc_dev, int32_t* orank_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "rr_index_search_masked": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
     "rr_index_search_ex": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64, _P, _P, c_int64, _P]),
     "rr_index_search_host": (c_int, [c_void_p, _P, c_int64, c_int, _P, _P]),
+    "rr_federation_search": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int64, c_int, _P, c_int64, _P, _P,
+                                     c_int64, _P]),
     "rr_index_get_stats": (c_int, [c_void_p, POINTER(IndexStats), c_int]),
     "rr_index_tc_qtile": (c_int, [c_void_p]),
     "rr_index_debug_tc_scan": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, POINTER(c_int), POINTER(c_int), _P]),
@@ -64,6 +66,8 @@ _SIGNATURES = {
     "rr_router_set_tables": (c_int, [c_void_p, c_int, c_int, c_int, _P, _P, _P, c_int, _P, _P]),
     "rr_router_select": (c_int, [c_void_p, _P, c_int64, c_float, _P, _P, _P]),
     "rr_merge_topk": (c_int, [_P, _P, c_int64, c_int, c_int, c_int, _P, _P, _P, _P]),
+    "rr_merge_topk_segments": (c_int, [_P, _P, c_int64, c_int, c_int, c_int64, c_int64, c_int, c_int, c_int,
+                                       _P, _P, _P, _P, _P, _P]),
 }
 
 

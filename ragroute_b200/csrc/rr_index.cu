@@ -24,6 +24,7 @@
 // Every stage after `finalize` is launched unconditionally and exits at once when no
 // query needs it.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -102,24 +103,59 @@ rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
     }
 }
 
-// Large-batch path: compact the ROUTED queries of a chunk (<= RR_GEMM_QCHUNK) to the front.  cpos[b] =
-// row of query b in the bf16 query buffer: routed queries keep their order in [0, n_active), unrouted
-// ones follow in [n_active, nq) (their rows are zero).  One block of 1024 threads, kCompactPer
-// consecutive queries per thread.
+// ---- batched launches ---------------------------------------------------------------------------
+// A routed step searches S sources for the same batch (the reference's fan-out,
+// /root/reference/ragroute/http_server.py:200-209).  Every stage that is not a scan runs as ONE
+// launch for all sources of the step: blockIdx.y (blockIdx.x for `begin`, .z for the exact scan)
+// selects the source, whose arguments sit side by side in the kernel parameters.  A plain
+// index.search is the S = 1 case of the same code.
+constexpr int RR_FED_MAX = 8;  // sources per batched launch (larger federations run in groups)
+template <class T>
+struct rr_multi {
+    T s[RR_FED_MAX];
+};
+
+struct rr_prep_args {
+    const float* q;  // [nq, d]
+    const uint8_t* mask;
+    int64_t mask_stride;
+    uint16_t* qbf16;
+    float* qnorm;
+    uint8_t* active;
+    uint8_t* fail_flags;
+    int* fail_list;
+    rr_chunk_ctl* ctl;
+    int* cpos;  // large-batch path only
+    int nq;
+    int nq_pad;
+    int d;
+    int d_pad;
+    int exact_all;
+    int compact;  // large-batch path: compact the routed queries to the front
+};
+
+// First launch of a chunk, one block per source: zero the chunk's control block and, on the large-batch
+// path, compact the ROUTED queries (<= RR_GEMM_QCHUNK) to the front.  cpos[b] = row of query b in the
+// bf16 query buffer: routed queries keep their order in [0, n_active), unrouted ones follow in
+// [n_active, nq) (their rows are zero).  1024 threads, kCompactPer consecutive queries per thread.
 constexpr int kCompactPer = RR_GEMM_QCHUNK / 1024;
 static_assert(RR_GEMM_QCHUNK % 1024 == 0 && kCompactPer >= 1 && kCompactPer <= 8, "compaction block covers the chunk");
 
 __global__ void __launch_bounds__(1024)
-rr_compact_queries_kernel(const uint8_t* __restrict__ mask, int64_t mask_stride, int nq, int* __restrict__ cpos,
-                          rr_chunk_ctl* ctl) {
+rr_begin_chunk_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
+    const rr_prep_args& a = m.s[blockIdx.x];
     __shared__ int warp_cnt[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid < (int)(sizeof(rr_chunk_ctl) / sizeof(int))) reinterpret_cast<int*>(a.ctl)[tid] = 0;
+    if (!a.compact) return;
+    const uint8_t* __restrict__ mask = a.mask;
+    const int nq = a.nq;
     bool act[kCompactPer];
     int mine = 0;
 #pragma unroll
     for (int u = 0; u < kCompactPer; ++u) {
         const int b = tid * kCompactPer + u;
-        act[u] = (b < nq) && (mask ? (mask[(int64_t)b * mask_stride] != 0) : true);
+        act[u] = (b < nq) && (mask ? (mask[(int64_t)b * a.mask_stride] != 0) : true);
         mine += act[u] ? 1 : 0;
     }
     // exclusive prefix of `mine` over the block
@@ -130,7 +166,7 @@ rr_compact_queries_kernel(const uint8_t* __restrict__ mask, int64_t mask_stride,
         if (lane >= o) incl += v;
     }
     if (lane == 31) warp_cnt[w] = incl;
-    __syncthreads();
+    __syncthreads();  // also orders the zeroing of ctl before n_active is set
     int before = incl - mine, total = 0;
     for (int i = 0; i < 32; ++i) {
         const int c = warp_cnt[i];
@@ -140,31 +176,30 @@ rr_compact_queries_kernel(const uint8_t* __restrict__ mask, int64_t mask_stride,
 #pragma unroll
     for (int u = 0; u < kCompactPer; ++u) {
         const int b = tid * kCompactPer + u;
-        if (b < nq) cpos[b] = act[u] ? before : total + (b - before);
+        if (b < nq) a.cpos[b] = act[u] ? before : total + (b - before);
         before += act[u] ? 1 : 0;
     }
-    if (tid == 0) ctl->n_active = total;
+    if (tid == 0) a.ctl->n_active = total;
 }
 
 // fp32 queries -> bf16 tile rows (zero padded to d_pad; rows >= nq zeroed), norms,
-// activity flags.  grid = nq_pad blocks.
+// activity flags.  grid = (max nq_pad, sources).
 __global__ void __launch_bounds__(128)
-rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
-                       const uint8_t* __restrict__ mask, int64_t mask_stride,
-                       uint16_t* __restrict__ qbf16, float* __restrict__ qnorm,
-                       uint8_t* __restrict__ active, uint8_t* __restrict__ fail_flags,
-                       int* __restrict__ fail_list, rr_chunk_ctl* ctl, int exact_all,
-                       const int* __restrict__ cpos) {
+rr_prep_queries_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
+    const rr_prep_args& a = m.s[blockIdx.y];
     const int b = blockIdx.x;
+    if (b >= a.nq_pad) return;
+    const int nq = a.nq, d = a.d, d_pad = a.d_pad;
+    const int* __restrict__ cpos = a.compact ? a.cpos : nullptr;
     // large-batch path: routed queries are compacted to the front of the bf16 buffer
-    uint16_t* out = qbf16 + (int64_t)((cpos && b < nq) ? cpos[b] : b) * d_pad;
+    uint16_t* out = a.qbf16 + (int64_t)((cpos && b < nq) ? cpos[b] : b) * d_pad;
     if (b >= nq) {
         for (int e = threadIdx.x; e < d_pad; e += blockDim.x) out[e] = 0;
-        if (threadIdx.x == 0) active[b] = 0;
+        if (threadIdx.x == 0) a.active[b] = 0;
         return;
     }
-    const bool act = mask ? (mask[(int64_t)b * mask_stride] != 0) : true;
-    const float* qr = q + (int64_t)b * d;
+    const bool act = a.mask ? (a.mask[(int64_t)b * a.mask_stride] != 0) : true;
+    const float* qr = a.q + (int64_t)b * d;
     __shared__ float part[4];
     float ss = 0.f;
     for (int e = threadIdx.x; e < d_pad; e += blockDim.x) {
@@ -181,14 +216,14 @@ rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
     if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
     __syncthreads();
     if (threadIdx.x == 0) {
-        qnorm[b] = sqrtf(part[0] + part[1] + part[2] + part[3]) * 1.000001f;
-        active[b] = act ? 1 : 0;
-        fail_flags[b] = 0;
+        a.qnorm[b] = sqrtf(part[0] + part[1] + part[2] + part[3]) * 1.000001f;
+        a.active[b] = act ? 1 : 0;
+        a.fail_flags[b] = 0;
         if (act) {
-            ctl->any_active = 1;
-            if (exact_all) {
-                fail_flags[b] = 1;
-                fail_list[atomicAdd(&ctl->n_fail, 1)] = b;
+            a.ctl->any_active = 1;
+            if (a.exact_all) {
+                a.fail_flags[b] = 1;
+                a.fail_list[atomicAdd(&a.ctl->n_fail, 1)] = b;
             }
         }
     }
@@ -199,13 +234,36 @@ rr_prep_queries_kernel(const float* __restrict__ q, int nq, int d, int d_pad,
 // fp64), score rounded once to fp32.  One warp per row; per-warp lists of depth
 // 32 per query, merged per block at the end.
 // cand layout: [query][block][32]
+struct rr_exact_args {
+    const uint16_t* hi;
+    const uint16_t* lo;
+    int64_t n_rows;
+    const float* q;
+    const int* fail_list;
+    const int* n_fail_ptr;
+    float* cand_s;
+    uint32_t* cand_r;
+    int64_t cand_stride;
+    int d;
+    int d_pad;
+    int qsub;
+};
+
 template <int QSUB>
 __global__ void __launch_bounds__(RR_EXACT_WARPS * 32)
-rr_exact_scan_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo,
-                     int64_t n_rows, int d_pad, const float* __restrict__ q, int d,
-                     const int* __restrict__ fail_list, const int* __restrict__ n_fail_ptr,
-                     int qsub, float* __restrict__ cand_s,
-                     uint32_t* __restrict__ cand_r, int64_t cand_stride) {
+rr_exact_scan_kernel(const __grid_constant__ rr_multi<rr_exact_args> m) {
+    const rr_exact_args& a = m.s[blockIdx.z];
+    if (a.n_rows <= 0) return;
+    const uint16_t* __restrict__ hi = a.hi;
+    const uint16_t* __restrict__ lo = a.lo;
+    const int64_t n_rows = a.n_rows;
+    const int d_pad = a.d_pad, d = a.d, qsub = a.qsub;
+    const float* __restrict__ q = a.q;
+    const int* __restrict__ fail_list = a.fail_list;
+    float* __restrict__ cand_s = a.cand_s;
+    uint32_t* __restrict__ cand_r = a.cand_r;
+    const int64_t cand_stride = a.cand_stride;
+    const int* n_fail_ptr = a.n_fail_ptr;
     const int n_fail = *n_fail_ptr;
     constexpr int M = RR_EXACT_LIST_DEPTH;
     constexpr int W = RR_EXACT_WARPS;
@@ -342,13 +400,22 @@ struct rr_finalize_args {
     float* theta_q;    // per query: threshold of the second pass when the certificate fails (or NULL)
     const int* cpos;   // large-batch path: candidate row of query qi (compacted); NULL = qi
     int lists_from_ctl;  // large-batch path: the number of lists is ctl->n_lists (decided on the device)
+    int enabled;       // 0: this source takes no part in the launch
 };
 
-constexpr int RR_FIN_THREADS = 256;
+constexpr int RR_FIN_THREADS = 512;
 constexpr int RR_FIN_MAXSEL = 256;
 
+// dynamic shared memory of a finalize block: the query (RESCORE) + the staged candidate lists
+static size_t rr_finalize_smem(bool rescore, int d_pad, int64_t cand_stride) {
+    return (rescore ? (size_t)d_pad * sizeof(float) : 0) + (size_t)cand_stride * 8;
+}
+
 template <bool RESCORE>
-__global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize_args a) {
+__global__ void __launch_bounds__(RR_FIN_THREADS)
+rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
+    const rr_finalize_args& a = m.s[blockIdx.y];
+    if (!a.enabled) return;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     float* Dq = a.D + (int64_t)qi * a.out_stride;
@@ -379,11 +446,14 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     __shared__ float s_red[RR_FIN_THREADS / 32];
     __shared__ float sel_s[RR_FIN_MAXSEL];
     __shared__ uint32_t sel_r[RR_FIN_MAXSEL];
-    extern __shared__ __align__(16) float q_sm[];  // [d_pad] (RESCORE only)
+    extern __shared__ __align__(16) unsigned char fin_sm[];
+    float* q_sm = reinterpret_cast<float*>(fin_sm);                               // [d_pad] (RESCORE only)
+    float* cs = reinterpret_cast<float*>(fin_sm) + (RESCORE ? a.d_pad : 0);       // [n_cand] staged scores
+    uint32_t* cr = reinterpret_cast<uint32_t*>(cs + a.cand_stride);               // [n_cand] staged rows
 
     const int crow = (RESCORE && a.cpos) ? a.cpos[qi] : qi;
-    const float* cs = a.cand_s + (int64_t)crow * a.cand_stride;
-    const uint32_t* cr = a.cand_r + (int64_t)crow * a.cand_stride;
+    const float* gs = a.cand_s + (int64_t)crow * a.cand_stride;
+    const uint32_t* gr = a.cand_r + (int64_t)crow * a.cand_stride;
     const int n_lists = (RESCORE && a.lists_from_ctl) ? a.ctl->n_lists : a.n_lists;
     const int n_cand = n_lists * a.depth;
 
@@ -398,18 +468,39 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
         const float* qr = a.q + (int64_t)qi * a.d;
         for (int e = tid; e < a.d_pad; e += blockDim.x) q_sm[e] = (e < a.d) ? qr[e] : 0.f;
     }
-    __syncthreads();
-
-    // T = largest tail of a full list (every dropped row scores <= T); n_valid
+    // stage the lists once (the select below makes 5-9 passes over them); count the occupied slots and take
+    // T = largest tail of a full list (every row a list dropped scores <= its tail)
     float T = RR_NEG_INF;
     int nv = 0;
-    for (int l = tid; l < n_lists; l += blockDim.x) {
-        const int64_t o = (int64_t)l * a.depth + a.depth - 1;
-        if (cr[o] != RR_NO_ROW) T = fmaxf(T, cs[o]);
+    {
+        constexpr int U = 4;
+        const int depth_m1 = a.depth - 1;
+        for (int i0 = tid; i0 < n_cand; i0 += RR_FIN_THREADS * U) {
+            float vs[U];
+            uint32_t vr[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * RR_FIN_THREADS;
+                vs[u] = (i < n_cand) ? __ldg(gs + i) : RR_NEG_INF;
+                vr[u] = (i < n_cand) ? __ldg(gr + i) : RR_NO_ROW;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int i = i0 + u * RR_FIN_THREADS;
+                if (i < n_cand) {
+                    cs[i] = vs[u];
+                    cr[i] = vr[u];
+                    if (vr[u] != RR_NO_ROW) {
+                        ++nv;
+                        if ((i & depth_m1) == depth_m1) T = fmaxf(T, vs[u]);  // list depths are powers of two
+                    }
+                }
+            }
+        }
     }
-    for (int i = tid; i < n_cand; i += blockDim.x) nv += (cr[i] != RR_NO_ROW);
     T = rr_warp_max(T);
     for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(RR_FULL, nv, o);
+    __syncthreads();  // s_nvalid is zero, the staged lists are visible
     if (lane == 0) {
         s_red[w] = T;
         atomicAdd(&s_nvalid, nv);
@@ -430,7 +521,7 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     if (kp > 0) {
         for (int pass = 0; pass < NPASS; ++pass) {
             const int shift = (NPASS - 1 - pass) * 8;
-            hist[tid] = 0;  // RR_FIN_THREADS == 256
+            if (tid < 256) hist[tid] = 0;
             __syncthreads();
             const unsigned long long prefix = s_prefix, mask = s_mask;
             for (int i = tid; i < n_cand; i += blockDim.x) {
@@ -511,42 +602,57 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
     __syncthreads();
 
     if (RESCORE) {
-        // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation.  One warp per row,
-        // RB rows per warp in flight at once (the gathers are random 2 x d_pad*2-byte reads: latency-bound)
-        constexpr int RB = 4;
+        // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation.  One warp per row, RB rows x
+        // CH chunks of 256 dimensions per warp in flight at once (the gathers are random 16-byte reads of
+        // both planes: latency-bound, so 16 warps x 12 loads cover 128 rows x 768 dims in 4 round trips)
+        constexpr int RB = 2, CH = 3;
         constexpr int NW = RR_FIN_THREADS / 32;
         for (int i0 = w * RB; i0 < kp; i0 += NW * RB) {
             double acc[RB];
+            int64_t rowo[RB];
 #pragma unroll
-            for (int r = 0; r < RB; ++r) acc[r] = 0.0;
-            for (int e0 = lane * 8; e0 < a.d_pad; e0 += 256) {
-                uint4 hv[RB], lv[RB];
+            for (int r = 0; r < RB; ++r) {
+                acc[r] = 0.0;
+                rowo[r] = (int64_t)sel_r[min(i0 + r, kp - 1)] * a.d_pad;
+            }
+            for (int e0 = lane * 8; e0 < a.d_pad; e0 += 256 * CH) {
+                uint4 hv[RB][CH], lv[RB][CH];
 #pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    const int i = min(i0 + r, kp - 1);
-                    const int64_t row = sel_r[i];
-                    hv[r] = __ldg(reinterpret_cast<const uint4*>(a.hi + row * a.d_pad) + (e0 >> 3));
-                    lv[r] = __ldg(reinterpret_cast<const uint4*>(a.lo + row * a.d_pad) + (e0 >> 3));
+                for (int c = 0; c < CH; ++c) {
+                    const int e = e0 + 256 * c;
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) {
+                        if (e < a.d_pad) {
+                            hv[r][c] = __ldg(reinterpret_cast<const uint4*>(a.hi + rowo[r]) + (e >> 3));
+                            lv[r][c] = __ldg(reinterpret_cast<const uint4*>(a.lo + rowo[r]) + (e >> 3));
+                        }
+                    }
                 }
-                const float4 qa = *reinterpret_cast<const float4*>(q_sm + e0);
-                const float4 qb = *reinterpret_cast<const float4*>(q_sm + e0 + 4);
 #pragma unroll
-                for (int r = 0; r < RB; ++r) {
-                    double s_ = acc[r];
-                    float2 t;
-                    t = rr_join_f32x2(hv[r].x, lv[r].x);
-                    s_ = fma((double)t.x, (double)qa.x, s_);
-                    s_ = fma((double)t.y, (double)qa.y, s_);
-                    t = rr_join_f32x2(hv[r].y, lv[r].y);
-                    s_ = fma((double)t.x, (double)qa.z, s_);
-                    s_ = fma((double)t.y, (double)qa.w, s_);
-                    t = rr_join_f32x2(hv[r].z, lv[r].z);
-                    s_ = fma((double)t.x, (double)qb.x, s_);
-                    s_ = fma((double)t.y, (double)qb.y, s_);
-                    t = rr_join_f32x2(hv[r].w, lv[r].w);
-                    s_ = fma((double)t.x, (double)qb.z, s_);
-                    s_ = fma((double)t.y, (double)qb.w, s_);
-                    acc[r] = s_;
+                for (int c = 0; c < CH; ++c) {
+                    const int e = e0 + 256 * c;
+                    if (e < a.d_pad) {
+                        const float4 qa = *reinterpret_cast<const float4*>(q_sm + e);
+                        const float4 qb = *reinterpret_cast<const float4*>(q_sm + e + 4);
+#pragma unroll
+                        for (int r = 0; r < RB; ++r) {
+                            double s_ = acc[r];
+                            float2 t;
+                            t = rr_join_f32x2(hv[r][c].x, lv[r][c].x);
+                            s_ = fma((double)t.x, (double)qa.x, s_);
+                            s_ = fma((double)t.y, (double)qa.y, s_);
+                            t = rr_join_f32x2(hv[r][c].y, lv[r][c].y);
+                            s_ = fma((double)t.x, (double)qa.z, s_);
+                            s_ = fma((double)t.y, (double)qa.w, s_);
+                            t = rr_join_f32x2(hv[r][c].z, lv[r][c].z);
+                            s_ = fma((double)t.x, (double)qb.x, s_);
+                            s_ = fma((double)t.y, (double)qb.y, s_);
+                            t = rr_join_f32x2(hv[r][c].w, lv[r][c].w);
+                            s_ = fma((double)t.x, (double)qb.z, s_);
+                            s_ = fma((double)t.y, (double)qb.w, s_);
+                            acc[r] = s_;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -617,29 +723,44 @@ __global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_kernel(rr_finalize
 // ---- second pass ("collect") for the queries whose certificate failed --------------------------
 // Gather their bf16 rows (in fail_list order) into the second query buffer, hand their thresholds to
 // the scan, zero their row counters.  grid = rows of the second buffer, 128 threads.
+struct rr_prep_collect_args {
+    const uint16_t* qbf16;
+    const int* cpos;
+    const int* fail_list;
+    const float* theta_q;
+    const rr_chunk_ctl* ctl;
+    uint16_t* qbf2;
+    float* theta2;
+    int* col_cnt;
+    rr_chunk_ctl* ctl2;
+    int d_pad;
+    int nq;
+    int nq_pad2;  // 0: this source has no second pass
+};
+
 __global__ void __launch_bounds__(128)
-rr_prep_collect_kernel(const uint16_t* __restrict__ qbf16, const int* __restrict__ cpos, int d_pad,
-                       const int* __restrict__ fail_list, const float* __restrict__ theta_q,
-                       const rr_chunk_ctl* __restrict__ ctl, uint16_t* __restrict__ qbf2, float* __restrict__ theta2,
-                       int* __restrict__ col_cnt, rr_chunk_ctl* ctl2, int nq) {
+rr_prep_collect_kernel(const __grid_constant__ rr_multi<rr_prep_collect_args> m) {
+    const rr_prep_collect_args& a = m.s[blockIdx.y];
     const int i = blockIdx.x;
-    const int n_fail = ctl->n_fail;
+    if (i >= a.nq_pad2) return;
+    const int d_pad = a.d_pad;
+    const int n_fail = a.ctl->n_fail;
     if (i == 0 && threadIdx.x == 0) {
-        ctl2->n_active = n_fail;
-        ctl2->any_active = n_fail > 0;
+        a.ctl2->n_active = n_fail;
+        a.ctl2->any_active = n_fail > 0;
     }
     if (n_fail == 0) return;  // nothing failed: the scan that follows exits at once, leave the buffer alone
-    uint4* out = reinterpret_cast<uint4*>(qbf2 + (int64_t)i * d_pad);
+    uint4* out = reinterpret_cast<uint4*>(a.qbf2 + (int64_t)i * d_pad);
     if (i < n_fail) {
-        const int qi = fail_list[i];
-        const uint4* in = reinterpret_cast<const uint4*>(qbf16 + (int64_t)(cpos ? cpos[qi] : qi) * d_pad);
+        const int qi = a.fail_list[i];
+        const uint4* in = reinterpret_cast<const uint4*>(a.qbf16 + (int64_t)(a.cpos ? a.cpos[qi] : qi) * d_pad);
         for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = in[e];
-        if (threadIdx.x == 0) theta2[i] = theta_q[qi];
+        if (threadIdx.x == 0) a.theta2[i] = a.theta_q[qi];
     } else {
         for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) theta2[i] = __builtin_huge_valf();
+        if (threadIdx.x == 0) a.theta2[i] = __builtin_huge_valf();
     }
-    if (threadIdx.x == 0 && i < nq) col_cnt[i] = 0;
+    if (threadIdx.x == 0 && i < a.nq) a.col_cnt[i] = 0;
 }
 
 constexpr int RR_COLLECT_CAP = 2048;  // rows a failing query may collect before it goes to the exact scan
@@ -662,14 +783,17 @@ struct rr_collect_fin_args {
     float* D;
     int64_t* I;
     int64_t out_stride;
+    int enabled;
 };
 
 // One block per failing query: every row that can possibly belong to its top-k was collected; score
 // them exactly (fp32 rows rebuilt from the planes, fp64 accumulate) and keep the k best by
 // (score desc, row asc) -- no certificate needed.  A query whose list overflowed goes to the exact scan.
-__global__ void __launch_bounds__(RR_FIN_THREADS) rr_finalize_collect_kernel(rr_collect_fin_args a) {
+__global__ void __launch_bounds__(RR_FIN_THREADS)
+rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args> m) {
+    const rr_collect_fin_args& a = m.s[blockIdx.y];
     const int i = blockIdx.x;
-    if (i >= a.ctl->n_fail) return;
+    if (!a.enabled || i >= a.ctl->n_fail) return;
     const int qi = a.fail_list[i];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cnt = a.col_cnt[i];
@@ -964,6 +1088,8 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
         RR_REQUIRE(value == RR_PATH_AUTO || value == RR_PATH_SMALL || value == RR_PATH_GEMM || value == RR_PATH_GEMM_PAIR,
                    "scan_path must be 0 (auto), 1 (64-query passes), 2 (large-batch kernel) or 3 (large-batch, CTA pairs)");
         h->scan_path = (int)value;
+    } else if (!strcmp(name, "gemm_tmem_all")) {
+        h->gemm_tmem_all = value != 0;
     } else {
         rr_set_error("rr_index_set_param: unknown parameter '%s'", name);
         return RR_ERR_INVALID;
@@ -977,7 +1103,7 @@ static int rr_flush_events(rr_index* h) {
         float ms = 0.f;
         RR_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_pool[i], h->ev_pool[i + 1]));
         h->stats.scan_ms_total += ms;
-        h->stats.scan_launches += 1;
+        h->stats.scan_launches += h->ev_launches[i / 2];
     }
     h->ev_used = 0;
     return RR_OK;
@@ -1025,21 +1151,58 @@ static int rr_gemm_cta_group(const rr_index* h, int nq) {
     return nq > 2 * RR_GEMM_QTILE ? 2 : 1;
 }
 
-// one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch path) queries
-static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const uint8_t* mask_dev,
-                           int64_t mask_stride, float* D_dev, int64_t* I_dev, int64_t out_stride,
-                           cudaStream_t stream) {
-    const int qt = rr_tc_scan_qtile(h);  // 0: tc path unavailable for this d
-    const bool use_gemm = (h->mode == RR_MODE_AUTO) && h->n > 0 && rr_use_gemm_path(h, nq);
-    const bool use_tc = (h->mode == RR_MODE_AUTO) && qt > 0 && h->n > 0 && !use_gemm;
-    const int gemm_cg = use_gemm ? rr_gemm_cta_group(h, nq) : 1;
-    const int nq_pad = (int)rr_align_up((size_t)nq, use_gemm ? RR_GEMM_QTILE * gemm_cg : RR_TC_MAX_QTILE);
-    const int g_exact = h->sm_count * 2;
-    const int64_t cand_stride =
-        use_gemm ? std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
-                                     (int64_t)rr_gemm_scan_max_lists(h) * RR_GEMM_LIST_DEPTH)
-                 : std::max<int64_t>((int64_t)g_exact * RR_EXACT_LIST_DEPTH,
-                                     (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH);
+// Everything one source needs for one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch
+// path) queries: which scan it takes and where its scratch lives.
+struct rr_chunk_plan {
+    rr_index* h;
+    const float* q;
+    const uint8_t* mask;
+    int64_t mask_stride;
+    float* D;
+    int64_t* I;
+    int64_t out_stride;
+    bool use_gemm, use_tc, use_pass2;
+    int gemm_cg, cg2, nq_pad, nq_pad2, qt, g_exact, qsub;
+    size_t ex_smem;
+    int64_t cand_stride;
+    rr_chunk_ctl *ctl, *ctl2;
+    uint16_t *qbf, *qbf2;
+    float *qnorm, *theta_q, *theta2, *cand_s;
+    uint8_t *active, *fail_flags;
+    int *fail_list, *cpos, *col_cnt, *fail2_list;
+    uint32_t *col_rows, *cand_r;
+};
+
+static int rr_plan_chunk(rr_index* h, const float* q_dev, int nq, const uint8_t* mask_dev, int64_t mask_stride,
+                         float* D_dev, int64_t* I_dev, int64_t out_stride, cudaStream_t stream, rr_chunk_plan* p) {
+    p->h = h;
+    p->q = q_dev;
+    p->mask = mask_dev;
+    p->mask_stride = mask_stride;
+    p->D = D_dev;
+    p->I = I_dev;
+    p->out_stride = out_stride;
+    p->qt = rr_tc_scan_qtile(h);  // 0: tc path unavailable for this d
+    p->use_gemm = (h->mode == RR_MODE_AUTO) && h->n > 0 && rr_use_gemm_path(h, nq);
+    p->use_tc = (h->mode == RR_MODE_AUTO) && p->qt > 0 && h->n > 0 && !p->use_gemm;
+    p->gemm_cg = p->use_gemm ? rr_gemm_cta_group(h, nq) : 1;
+    p->nq_pad = (int)rr_align_up((size_t)nq, p->use_gemm ? RR_GEMM_QTILE * p->gemm_cg : RR_TC_MAX_QTILE);
+    p->g_exact = h->sm_count * 2;
+    p->cand_stride =
+        p->use_gemm ? std::max<int64_t>((int64_t)p->g_exact * RR_EXACT_LIST_DEPTH,
+                                        (int64_t)rr_gemm_scan_max_lists(h) * RR_GEMM_LIST_DEPTH)
+                    : std::max<int64_t>((int64_t)p->g_exact * RR_EXACT_LIST_DEPTH,
+                                        (int64_t)rr_tc_scan_num_lists(h) * RR_TC_LIST_DEPTH);
+    // second pass (queries whose certificate failed), only when the first pass was a tensor-core scan
+    p->use_pass2 = (p->use_tc || p->use_gemm) && rr_gemm_scan_supported(h);
+    p->cg2 = rr_gemm_cta_group(h, nq);
+    p->nq_pad2 = p->use_pass2 ? (int)rr_align_up((size_t)nq, (size_t)RR_GEMM_QTILE * p->cg2) : 0;
+    int qsub = RR_EXACT_MAX_QSUB;
+    while (qsub > 1 && (size_t)qsub * h->d_pad * sizeof(float) > (96u << 10)) qsub >>= 1;
+    p->qsub = qsub;
+    p->ex_smem = (size_t)qsub * h->d_pad * sizeof(float) + (size_t)RR_EXACT_WARPS * qsub * RR_EXACT_LIST_DEPTH * 8 +
+                 (size_t)RR_EXACT_WARPS * qsub * sizeof(float) + (size_t)qsub * sizeof(int);
+    RR_REQUIRE(p->ex_smem <= (200u << 10), "dimension %d too large for the exact scan kernel", h->d);
 
     // carve the scratch block
     size_t off = 0;
@@ -1048,6 +1211,7 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
         off = rr_align_up(off + bytes, 1024);
         return o;
     };
+    const int nq_pad = p->nq_pad, nq_pad2 = p->nq_pad2;
     const size_t o_ctl = carve(sizeof(rr_chunk_ctl));
     const size_t o_qbf = carve((size_t)nq_pad * h->d_pad * sizeof(uint16_t));
     const size_t o_qn = carve((size_t)nq_pad * sizeof(float));
@@ -1055,203 +1219,378 @@ static int rr_search_chunk(rr_index* h, const float* q_dev, int nq, int k, const
     const size_t o_ff = carve((size_t)nq_pad);
     const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
     const size_t o_cp = carve((size_t)nq_pad * sizeof(int));
-    // second pass (queries whose certificate failed), only when the first pass was a tensor-core scan
-    const bool use_pass2 = (use_tc || use_gemm) && rr_gemm_scan_supported(h);
-    const int cg2 = rr_gemm_cta_group(h, nq);
-    const int nq_pad2 = use_pass2 ? (int)rr_align_up((size_t)nq, (size_t)RR_GEMM_QTILE * cg2) : 0;
     const size_t o_ctl2 = carve(sizeof(rr_chunk_ctl));
     const size_t o_qb2 = carve((size_t)nq_pad2 * h->d_pad * sizeof(uint16_t));
     const size_t o_thq = carve((size_t)nq_pad * sizeof(float));
     const size_t o_th2 = carve((size_t)nq_pad2 * sizeof(float));
     const size_t o_cc = carve((size_t)nq_pad2 * sizeof(int));
     const size_t o_f2 = carve((size_t)nq_pad * sizeof(int));
-    const size_t o_cr2 = carve(use_pass2 ? (size_t)nq * RR_COLLECT_CAP * sizeof(uint32_t) : 0);
-    const size_t o_cs = carve((size_t)nq * cand_stride * sizeof(float));
-    const size_t o_cr = carve((size_t)nq * cand_stride * sizeof(uint32_t));
+    const size_t o_cr2 = carve(p->use_pass2 ? (size_t)nq * RR_COLLECT_CAP * sizeof(uint32_t) : 0);
+    const size_t o_cs = carve((size_t)nq * p->cand_stride * sizeof(float));
+    const size_t o_cr = carve((size_t)nq * p->cand_stride * sizeof(uint32_t));
     if (off > h->scratch_bytes) {
         RR_CUDA_CHECK(cudaStreamSynchronize(stream));
         int rc = rr_grow(&h->scratch, &h->scratch_bytes, off);
         if (rc != RR_OK) return rc;
     }
     char* base = (char*)h->scratch;
-    rr_chunk_ctl* ctl = (rr_chunk_ctl*)(base + o_ctl);
-    uint16_t* qbf = (uint16_t*)(base + o_qbf);
-    float* qnorm = (float*)(base + o_qn);
-    uint8_t* active = (uint8_t*)(base + o_act);
-    uint8_t* fail_flags = (uint8_t*)(base + o_ff);
-    int* fail_list = (int*)(base + o_fl);
-    int* cpos = (int*)(base + o_cp);
-    rr_chunk_ctl* ctl2 = (rr_chunk_ctl*)(base + o_ctl2);
-    uint16_t* qbf2 = (uint16_t*)(base + o_qb2);
-    float* theta_q = (float*)(base + o_thq);
-    float* theta2 = (float*)(base + o_th2);
-    int* col_cnt = (int*)(base + o_cc);
-    int* fail2_list = (int*)(base + o_f2);
-    uint32_t* col_rows = (uint32_t*)(base + o_cr2);
-    float* cand_s = (float*)(base + o_cs);
-    uint32_t* cand_r = (uint32_t*)(base + o_cr);
+    p->ctl = (rr_chunk_ctl*)(base + o_ctl);
+    p->qbf = (uint16_t*)(base + o_qbf);
+    p->qnorm = (float*)(base + o_qn);
+    p->active = (uint8_t*)(base + o_act);
+    p->fail_flags = (uint8_t*)(base + o_ff);
+    p->fail_list = (int*)(base + o_fl);
+    p->cpos = (int*)(base + o_cp);
+    p->ctl2 = (rr_chunk_ctl*)(base + o_ctl2);
+    p->qbf2 = (uint16_t*)(base + o_qb2);
+    p->theta_q = (float*)(base + o_thq);
+    p->theta2 = (float*)(base + o_th2);
+    p->col_cnt = (int*)(base + o_cc);
+    p->fail2_list = (int*)(base + o_f2);
+    p->col_rows = (uint32_t*)(base + o_cr2);
+    p->cand_s = (float*)(base + o_cs);
+    p->cand_r = (uint32_t*)(base + o_cr);
+    return RR_OK;
+}
 
-    RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
-    if (use_gemm) {
-        rr_compact_queries_kernel<<<1, 1024, 0, stream>>>(mask_dev, mask_stride, nq, cpos, ctl);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_count_launch(1);
-    }
-    rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, mask_dev, mask_stride,
-                                                       qbf, qnorm, active, fail_flags, fail_list, ctl,
-                                                       (use_tc || use_gemm) ? 0 : 1, use_gemm ? cpos : nullptr);
-    RR_CUDA_CHECK(cudaGetLastError());
-    rr_count_launch(1);
+// never synchronise inside a search: a full event pool just stops recording
+static int rr_prof_begin(rr_index* h, cudaStream_t stream, bool* on) {
+    *on = h->profile != 0 && h->ev_used + 2 <= rr_index::kEvPool;
+    if (!*on) return RR_OK;
+    for (int i = 0; i < 2; ++i)
+        if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
+    RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
+    return RR_OK;
+}
+static int rr_prof_end(rr_index* h, cudaStream_t stream, bool on, int launches) {
+    if (!on) return RR_OK;
+    RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
+    h->ev_launches[h->ev_used / 2] = launches;
+    h->ev_used += 2;
+    return RR_OK;
+}
 
-    rr_finalize_args fa;
-    fa.cand_s = cand_s;
-    fa.cand_r = cand_r;
-    fa.cand_stride = cand_stride;
-    fa.k = k;
-    fa.kprime = std::max(h->kprime, k);
-    fa.q = q_dev;
-    fa.qnorm = qnorm;
-    fa.hi = h->hi;
-    fa.lo = h->lo;
-    fa.d = h->d;
-    fa.d_pad = h->d_pad;
-    fa.max_norm_bits = h->max_norm_bits;
-    fa.id_offset = h->id_offset;
-    fa.D = D_dev;
-    fa.I = I_dev;
-    fa.out_stride = out_stride;
-    fa.active = active;
-    fa.fail_flags = fail_flags;
-    fa.fail_list = fail_list;
-    fa.ctl = ctl;
-    fa.nfail_total = h->d_nfail_total;
-    fa.pad_inactive = (use_tc || use_gemm) ? 0 : 1;
-    fa.cpos = nullptr;
-    fa.lists_from_ctl = 0;
-    fa.theta_q = use_pass2 ? theta_q : nullptr;
-
-    if (use_gemm) {
-        // one launch covers the whole chunk: queries stationary in TMEM, corpus read once
-        const bool prof = h->profile != 0 && h->ev_used + 2 <= rr_index::kEvPool;
-        if (prof) {
-            for (int i = 0; i < 2; ++i)
-                if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
-            RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
-        }
-        int rc = rr_gemm_scan_launch(h, qbf, nq, gemm_cg, ctl, cand_s, cand_r, cand_stride,
-                                     prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr, nullptr,
-                                     stream);
-        if (rc != RR_OK) return rc;
-        rr_count_launch(1);
-        if (prof) {
-            RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
-            h->ev_used += 2;
-        }
-        fa.n_lists = 0;
-        fa.lists_from_ctl = 1;
-        fa.cpos = cpos;
-        fa.depth = RR_GEMM_LIST_DEPTH;
-        rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_count_launch(1);
-    }
-    if (use_tc) {
-        for (int p0 = 0; p0 < nq; p0 += qt) {
-            const int nqt = std::min(qt, nq - p0);
-            int n_lists = 0;
-            // never synchronise inside a search: a full pool just stops recording
-            const bool prof = h->profile != 0 && h->ev_used + 2 <= rr_index::kEvPool;
-            if (prof) {
-                for (int i = 0; i < 2; ++i)
-                    if (!h->ev_pool[h->ev_used + i]) RR_CUDA_CHECK(cudaEventCreate(&h->ev_pool[h->ev_used + i]));
-                RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used], stream));
-            }
-            int rc = rr_tc_scan_launch(h, qbf, nq_pad, p0, nqt, active + p0, &ctl->any_active,
-                                       cand_s + (size_t)p0 * cand_stride, cand_r + (size_t)p0 * cand_stride,
-                                       cand_stride, &n_lists,
-                                       prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr,
-                                       stream);
-            if (rc != RR_OK) return rc;
-            rr_count_launch(1);
-            if (prof) {
-                RR_CUDA_CHECK(cudaEventRecord(h->ev_pool[h->ev_used + 1], stream));
-                h->ev_used += 2;
-            }
-            fa.n_lists = n_lists;
-            fa.depth = RR_TC_LIST_DEPTH;
-        }
-        rr_finalize_kernel<true><<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(fa);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_count_launch(1);
+// One chunk of queries against S <= RR_FED_MAX sources (all on one device and stream): the scans are one
+// launch per source, every other stage is one launch for all of them.
+static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t stream) {
+    int max_nq_pad = 0, max_nq_pad2 = 0, max_dpad = 0;
+    size_t max_ex_smem = 0;
+    bool any_first = false, any_pass2 = false, any_rows = false;
+    for (int s = 0; s < S; ++s) {
+        const rr_chunk_plan& p = plans[s];
+        max_nq_pad = std::max(max_nq_pad, p.nq_pad);
+        max_nq_pad2 = std::max(max_nq_pad2, p.nq_pad2);
+        max_dpad = std::max(max_dpad, p.h->d_pad);
+        max_ex_smem = std::max(max_ex_smem, p.ex_smem);
+        any_first |= p.use_tc || p.use_gemm;
+        any_pass2 |= p.use_pass2;
+        any_rows |= p.h->n > 0;
     }
 
-    // second pass over the queries whose certificate failed: the tensor-core scan again, this time
-    // reporting every row above a per-query threshold that provably keeps the whole exact top-k; then
-    // exact scores of those rows.  All three launches exit at once when nothing failed.
-    const int* exact_list = fail_list;
-    const int* exact_count = &ctl->n_fail;
-    if (use_pass2) {
-        rr_prep_collect_kernel<<<nq_pad2, 128, 0, stream>>>(qbf, use_gemm ? cpos : nullptr, h->d_pad, fail_list, theta_q,
-                                                            ctl, qbf2, theta2, col_cnt, ctl2, nq);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_collect_args ca;
-        ca.theta = theta2;
-        ca.rows = col_rows;
-        ca.cnt = col_cnt;
-        ca.cap = RR_COLLECT_CAP;
-        int rc = rr_gemm_scan_launch(h, qbf2, nq, cg2, ctl2, nullptr, nullptr, 0, nullptr, &ca, stream);
-        if (rc != RR_OK) return rc;
-        rr_collect_fin_args cf;
-        cf.col_rows = col_rows;
-        cf.col_cnt = col_cnt;
-        cf.fail_list = fail_list;
-        cf.ctl = ctl;
-        cf.fail2_list = fail2_list;
-        cf.fail_flags = fail_flags;
-        cf.n_exact_total = h->d_nfail_total + 1;
-        cf.k = k;
-        cf.q = q_dev;
-        cf.hi = h->hi;
-        cf.lo = h->lo;
-        cf.d = h->d;
-        cf.d_pad = h->d_pad;
-        cf.id_offset = h->id_offset;
-        cf.D = D_dev;
-        cf.I = I_dev;
-        cf.out_stride = out_stride;
-        rr_finalize_collect_kernel<<<nq, RR_FIN_THREADS, (size_t)h->d_pad * sizeof(float), stream>>>(cf);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_count_launch(3);
-        exact_list = fail2_list;
-        exact_count = &ctl->n_fail2;
-    }
-
-    // exact path over what is left (everything when there was no tensor-core pass); launches exit at once when empty
-    int qsub = RR_EXACT_MAX_QSUB;
-    while (qsub > 1 && (size_t)qsub * h->d_pad * sizeof(float) > (96u << 10)) qsub >>= 1;
-    const size_t ex_smem = (size_t)qsub * h->d_pad * sizeof(float) +
-                           (size_t)RR_EXACT_WARPS * qsub * RR_EXACT_LIST_DEPTH * 8 +
-                           (size_t)RR_EXACT_WARPS * qsub * sizeof(float) + (size_t)qsub * sizeof(int);
+    size_t fin_smem[2] = {0, 0};  // [RESCORE]
+    for (int s = 0; s < S; ++s)
+        for (int r = 0; r < 2; ++r)
+            fin_smem[r] = std::max(fin_smem[r], rr_finalize_smem(r != 0, plans[s].h->d_pad, plans[s].cand_stride));
+    RR_REQUIRE(fin_smem[1] <= (200u << 10), "dimension %d too large for the finalize kernel", max_dpad);
+    int dev = 0;
+    RR_CUDA_CHECK(cudaGetDevice(&dev));
     static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    if (!attr_done[dev & 63]) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_exact_scan_kernel<RR_EXACT_MAX_QSUB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        attr_done[h->device & 63] = true;
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        attr_done[dev & 63] = true;
     }
-    RR_REQUIRE(ex_smem <= (200u << 10), "dimension %d too large for the exact scan kernel", h->d);
-    if (h->n > 0) {
-        // one launch covers every sub-batch; blocks beyond the failing queries exit at once
-        const dim3 grid((unsigned)g_exact, (unsigned)std::min(4, (nq + qsub - 1) / qsub));
-        rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, ex_smem, stream>>>(
-            h->hi, h->lo, h->n, h->d_pad, q_dev, h->d, exact_list, exact_count, qsub, cand_s, cand_r, cand_stride);
+
+    rr_multi<rr_prep_args> pa;
+    memset(&pa, 0, sizeof(pa));
+    for (int s = 0; s < S; ++s) {
+        const rr_chunk_plan& p = plans[s];
+        rr_prep_args& a = pa.s[s];
+        a.q = p.q;
+        a.mask = p.mask;
+        a.mask_stride = p.mask_stride;
+        a.qbf16 = p.qbf;
+        a.qnorm = p.qnorm;
+        a.active = p.active;
+        a.fail_flags = p.fail_flags;
+        a.fail_list = p.fail_list;
+        a.ctl = p.ctl;
+        a.cpos = p.cpos;
+        a.nq = nq;
+        a.nq_pad = p.nq_pad;
+        a.d = p.h->d;
+        a.d_pad = p.h->d_pad;
+        a.exact_all = (p.use_tc || p.use_gemm) ? 0 : 1;
+        a.compact = p.use_gemm ? 1 : 0;
+    }
+    rr_begin_chunk_kernel<<<S, 1024, 0, stream>>>(pa);
+    RR_CUDA_CHECK(cudaGetLastError());
+    rr_prep_queries_kernel<<<dim3((unsigned)max_nq_pad, (unsigned)S), 128, 0, stream>>>(pa);
+    RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(2);
+
+    rr_multi<rr_finalize_args> fa;
+    memset(&fa, 0, sizeof(fa));
+    for (int s = 0; s < S; ++s) {
+        const rr_chunk_plan& p = plans[s];
+        rr_index* h = p.h;
+        rr_finalize_args& a = fa.s[s];
+        a.cand_s = p.cand_s;
+        a.cand_r = p.cand_r;
+        a.cand_stride = p.cand_stride;
+        a.k = k;
+        a.kprime = std::max(h->kprime, k);
+        a.q = p.q;
+        a.qnorm = p.qnorm;
+        a.hi = h->hi;
+        a.lo = h->lo;
+        a.d = h->d;
+        a.d_pad = h->d_pad;
+        a.max_norm_bits = h->max_norm_bits;
+        a.id_offset = h->id_offset;
+        a.D = p.D;
+        a.I = p.I;
+        a.out_stride = p.out_stride;
+        a.active = p.active;
+        a.fail_flags = p.fail_flags;
+        a.fail_list = p.fail_list;
+        a.ctl = p.ctl;
+        a.nfail_total = h->d_nfail_total;
+        a.pad_inactive = (p.use_tc || p.use_gemm) ? 0 : 1;
+        a.theta_q = p.use_pass2 ? p.theta_q : nullptr;
+        a.enabled = (p.use_tc || p.use_gemm) ? 1 : 0;
+    }
+
+    // ---- first pass: bf16 tensor-core scan of every source, then one finalize for all of them.  The scans
+    // are chained by programmatic dependent launch (they touch disjoint memory): no gap and no idle SMs
+    // between them.  Profiling brackets the whole chain with one event pair.
+    rr_index* hprof = nullptr;
+    for (int s = 0; s < S && !hprof; ++s)
+        if ((plans[s].use_gemm || plans[s].use_tc) && plans[s].h->profile) hprof = plans[s].h;
+    bool prof = false;
+    if (hprof) {
+        int rc = rr_prof_begin(hprof, stream, &prof);
+        if (rc != RR_OK) return rc;
+    }
+    static const bool no_chain = getenv("RR_NO_SCAN_CHAIN") != nullptr;  // measurement knob
+    int chain_len = 0;
+    for (int s = 0; s < S; ++s) {
+        const rr_chunk_plan& p = plans[s];
+        rr_index* h = p.h;
+        rr_finalize_args& a = fa.s[s];
+        rr_scan_counters* ctr = prof ? reinterpret_cast<rr_scan_counters*>(h->d_nfail_total + 2) : nullptr;
+        if (p.use_gemm) {
+            // one launch covers the whole chunk: queries stationary in TMEM, corpus read once
+            int rc = rr_gemm_scan_launch(h, p.qbf, nq, p.gemm_cg, p.ctl, p.cand_s, p.cand_r, p.cand_stride, ctr, nullptr,
+                                         chain_len > 0 && !no_chain, stream);
+            if (rc != RR_OK) return rc;
+            rr_count_launch(1);
+            ++chain_len;
+            a.n_lists = 0;
+            a.lists_from_ctl = 1;
+            a.cpos = p.cpos;
+            a.depth = RR_GEMM_LIST_DEPTH;
+        } else if (p.use_tc) {
+            for (int p0 = 0; p0 < nq; p0 += p.qt) {
+                const int nqt = std::min(p.qt, nq - p0);
+                int n_lists = 0;
+                int rc = rr_tc_scan_launch(h, p.qbf, p.nq_pad, p0, nqt, p.active + p0, &p.ctl->any_active,
+                                           p.cand_s + (size_t)p0 * p.cand_stride, p.cand_r + (size_t)p0 * p.cand_stride,
+                                           p.cand_stride, &n_lists, ctr, chain_len > 0 && !no_chain, stream);
+                if (rc != RR_OK) return rc;
+                rr_count_launch(1);
+                ++chain_len;
+                a.n_lists = n_lists;
+                a.depth = RR_TC_LIST_DEPTH;
+            }
+        }
+    }
+    if (hprof) {
+        int rc = rr_prof_end(hprof, stream, prof, chain_len);
+        if (rc != RR_OK) return rc;
+    }
+    if (any_first) {
+        rr_finalize_kernel<true><<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS, fin_smem[1], stream>>>(fa);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
     }
-    fa.n_lists = (h->n > 0) ? g_exact : 0;
-    fa.depth = RR_EXACT_LIST_DEPTH;
-    rr_finalize_kernel<false><<<nq, RR_FIN_THREADS, 0, stream>>>(fa);
+
+    // ---- second pass over the queries whose certificate failed: the tensor-core scan again, this time
+    // reporting every row above a per-query threshold that provably keeps the whole exact top-k; then
+    // exact scores of those rows.  All launches exit at once when nothing failed.
+    if (any_pass2) {
+        rr_multi<rr_prep_collect_args> pc;
+        rr_multi<rr_collect_fin_args> cf;
+        memset(&pc, 0, sizeof(pc));
+        memset(&cf, 0, sizeof(cf));
+        for (int s = 0; s < S; ++s) {
+            const rr_chunk_plan& p = plans[s];
+            if (!p.use_pass2) continue;
+            rr_index* h = p.h;
+            rr_prep_collect_args& a = pc.s[s];
+            a.qbf16 = p.qbf;
+            a.cpos = p.use_gemm ? p.cpos : nullptr;
+            a.fail_list = p.fail_list;
+            a.theta_q = p.theta_q;
+            a.ctl = p.ctl;
+            a.qbf2 = p.qbf2;
+            a.theta2 = p.theta2;
+            a.col_cnt = p.col_cnt;
+            a.ctl2 = p.ctl2;
+            a.d_pad = h->d_pad;
+            a.nq = nq;
+            a.nq_pad2 = p.nq_pad2;
+            rr_collect_fin_args& c = cf.s[s];
+            c.col_rows = p.col_rows;
+            c.col_cnt = p.col_cnt;
+            c.fail_list = p.fail_list;
+            c.ctl = p.ctl;
+            c.fail2_list = p.fail2_list;
+            c.fail_flags = p.fail_flags;
+            c.n_exact_total = h->d_nfail_total + 1;
+            c.k = k;
+            c.q = p.q;
+            c.hi = h->hi;
+            c.lo = h->lo;
+            c.d = h->d;
+            c.d_pad = h->d_pad;
+            c.id_offset = h->id_offset;
+            c.D = p.D;
+            c.I = p.I;
+            c.out_stride = p.out_stride;
+            c.enabled = 1;
+        }
+        rr_prep_collect_kernel<<<dim3((unsigned)max_nq_pad2, (unsigned)S), 128, 0, stream>>>(pc);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
+        int n_collect = 0;
+        for (int s = 0; s < S; ++s) {
+            const rr_chunk_plan& p = plans[s];
+            if (!p.use_pass2) continue;
+            rr_collect_args ca;
+            ca.theta = p.theta2;
+            ca.rows = p.col_rows;
+            ca.cnt = p.col_cnt;
+            ca.cap = RR_COLLECT_CAP;
+            int rc = rr_gemm_scan_launch(p.h, p.qbf2, nq, p.cg2, p.ctl2, nullptr, nullptr, 0, nullptr, &ca, n_collect > 0,
+                                         stream);
+            ++n_collect;
+            if (rc != RR_OK) return rc;
+            rr_count_launch(1);
+        }
+        rr_finalize_collect_kernel<<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS,
+                                     (size_t)max_dpad * sizeof(float), stream>>>(cf);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
+    }
+
+    // ---- exact path over what is left (everything when there was no tensor-core pass); launches exit
+    // at once when empty
+    if (any_rows) {
+        rr_multi<rr_exact_args> ea;
+        memset(&ea, 0, sizeof(ea));
+        int min_qsub = RR_EXACT_MAX_QSUB;
+        for (int s = 0; s < S; ++s) {
+            const rr_chunk_plan& p = plans[s];
+            rr_exact_args& a = ea.s[s];
+            a.hi = p.h->hi;
+            a.lo = p.h->lo;
+            a.n_rows = p.h->n;
+            a.q = p.q;
+            a.fail_list = p.use_pass2 ? p.fail2_list : p.fail_list;
+            a.n_fail_ptr = p.use_pass2 ? &p.ctl->n_fail2 : &p.ctl->n_fail;
+            a.cand_s = p.cand_s;
+            a.cand_r = p.cand_r;
+            a.cand_stride = p.cand_stride;
+            a.d = p.h->d;
+            a.d_pad = p.h->d_pad;
+            a.qsub = p.qsub;
+            min_qsub = std::min(min_qsub, p.qsub);
+        }
+        // one launch covers every sub-batch of every source; blocks beyond the failing queries exit at once
+        const int g_exact = plans[0].g_exact;
+        const dim3 grid((unsigned)g_exact, (unsigned)std::min(4, (nq + min_qsub - 1) / min_qsub), (unsigned)S);
+        rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, max_ex_smem, stream>>>(ea);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(1);
+    }
+    for (int s = 0; s < S; ++s) {
+        rr_finalize_args& a = fa.s[s];
+        a.n_lists = (plans[s].h->n > 0) ? plans[s].g_exact : 0;
+        a.depth = RR_EXACT_LIST_DEPTH;
+        a.lists_from_ctl = 0;
+        a.cpos = nullptr;
+        a.enabled = 1;
+    }
+    rr_finalize_kernel<false><<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS, fin_smem[0], stream>>>(fa);
     RR_CUDA_CHECK(cudaGetLastError());
     rr_count_launch(1);
+    return RR_OK;
+}
+
+static int64_t rr_chunk_size(const rr_index* h, int64_t nq) {
+    return (h->mode == RR_MODE_AUTO && rr_use_gemm_path(h, nq)) ? RR_GEMM_QCHUNK : RR_QCHUNK;
+}
+
+extern "C" int rr_federation_search(rr_index_t* const* idx, int n_sources, const float* const* q_dev, int64_t nq,
+                                    int k, const uint8_t* mask_dev, int64_t mask_stride, float* D_dev,
+                                    int64_t* I_dev, int64_t out_stride, void* stream_) {
+    RR_REQUIRE(idx != nullptr && n_sources >= 1, "rr_federation_search: no sources");
+    RR_REQUIRE(nq >= 0, "rr_federation_search: negative nq");
+    RR_REQUIRE(k > 0, "rr_federation_search: k must be > 0 (got %d)", k);
+    if (k > RR_MAX_K) {
+        rr_set_error("rr_federation_search: k=%d > RR_MAX_K=%d is not implemented", k, RR_MAX_K);
+        return RR_ERR_UNSUPPORTED;
+    }
+    for (int s = 0; s < n_sources; ++s) {
+        RR_REQUIRE(idx[s] != nullptr, "rr_federation_search: source %d is NULL", s);
+        RR_REQUIRE(idx[s]->device == idx[0]->device, "rr_federation_search: sources live on different devices");
+        for (int t = 0; t < s; ++t)
+            RR_REQUIRE(idx[t] != idx[s], "rr_federation_search: source %d listed twice (handles are not re-entrant)", s);
+    }
+    if (nq == 0) return RR_OK;
+    RR_REQUIRE(q_dev && D_dev && I_dev, "rr_federation_search: NULL buffer");
+    for (int s = 0; s < n_sources; ++s) RR_REQUIRE(q_dev[s] != nullptr, "rr_federation_search: NULL queries for source %d", s);
+    RR_REQUIRE(mask_dev == nullptr || mask_stride >= n_sources, "rr_federation_search: mask stride < n_sources");
+    if (out_stride == 0) out_stride = (int64_t)n_sources * k;
+    RR_REQUIRE(out_stride >= (int64_t)n_sources * k, "rr_federation_search: out_stride < n_sources * k");
+    rr_device_guard g(idx[0]->device);
+    cudaStream_t stream = (cudaStream_t)stream_;
+
+    // sources that chunk the batch alike share their launches, RR_FED_MAX at a time
+    bool done[256] = {};
+    RR_REQUIRE(n_sources <= 256, "rr_federation_search: more than 256 sources");
+    for (int s0 = 0; s0 < n_sources; ++s0) {
+        if (done[s0]) continue;
+        const int64_t chunk = rr_chunk_size(idx[s0], nq);
+        int group[RR_FED_MAX], G = 0;
+        for (int s = s0; s < n_sources && G < RR_FED_MAX; ++s)
+            if (!done[s] && rr_chunk_size(idx[s], nq) == chunk) {
+                group[G++] = s;
+                done[s] = true;
+            }
+        for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
+            const int nqc = (int)std::min<int64_t>(chunk, nq - q0);
+            rr_chunk_plan plans[RR_FED_MAX];
+            for (int i = 0; i < G; ++i) {
+                const int s = group[i];
+                rr_index* h = idx[s];
+                int rc = rr_plan_chunk(h, q_dev[s] + (size_t)q0 * h->d, nqc,
+                                       mask_dev ? mask_dev + q0 * mask_stride + s : nullptr, mask_stride,
+                                       D_dev + (size_t)q0 * out_stride + (size_t)s * k,
+                                       I_dev + (size_t)q0 * out_stride + (size_t)s * k, out_stride, stream, &plans[i]);
+                if (rc != RR_OK) return rc;
+            }
+            int rc = rr_run_chunk(plans, G, nqc, k, stream);
+            if (rc != RR_OK) return rc;
+        }
+    }
+    for (int s = 0; s < n_sources; ++s) {
+        idx[s]->stats.searches += 1;
+        idx[s]->stats.queries += nq;
+    }
     return RR_OK;
 }
 
@@ -1272,13 +1611,15 @@ extern "C" int rr_index_search_ex(rr_index_t* h, const float* q_dev, int64_t nq,
     RR_REQUIRE(out_stride >= k, "rr_index_search: out_stride < k");
     rr_device_guard g(h->device);
     cudaStream_t stream = (cudaStream_t)stream_;
-    const int64_t chunk = (h->mode == RR_MODE_AUTO && rr_use_gemm_path(h, nq)) ? RR_GEMM_QCHUNK : RR_QCHUNK;
+    const int64_t chunk = rr_chunk_size(h, nq);
     for (int64_t q0 = 0; q0 < nq; q0 += chunk) {
         const int nqc = (int)std::min<int64_t>(chunk, nq - q0);
-        int rc = rr_search_chunk(h, q_dev + (size_t)q0 * h->d, nqc, k,
-                                 mask_dev ? mask_dev + q0 * mask_stride : nullptr, mask_stride,
-                                 D_dev + (size_t)q0 * out_stride, I_dev + (size_t)q0 * out_stride, out_stride,
-                                 stream);
+        rr_chunk_plan plan;
+        int rc = rr_plan_chunk(h, q_dev + (size_t)q0 * h->d, nqc, mask_dev ? mask_dev + q0 * mask_stride : nullptr,
+                               mask_stride, D_dev + (size_t)q0 * out_stride, I_dev + (size_t)q0 * out_stride,
+                               out_stride, stream, &plan);
+        if (rc != RR_OK) return rc;
+        rc = rr_run_chunk(&plan, 1, nqc, k, stream);
         if (rc != RR_OK) return rc;
     }
     h->stats.searches += 1;
@@ -1358,15 +1699,25 @@ extern "C" int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq,
     char* base = (char*)h->scratch;
     rr_chunk_ctl* ctl = (rr_chunk_ctl*)(base + o_ctl);
     RR_CUDA_CHECK(cudaMemsetAsync(ctl, 0, sizeof(rr_chunk_ctl), stream));
-    rr_prep_queries_kernel<<<nq_pad, 128, 0, stream>>>(q_dev, nq, h->d, h->d_pad, nullptr, 0,
-                                                       (uint16_t*)(base + o_qbf), (float*)(base + o_qn),
-                                                       (uint8_t*)(base + o_act), (uint8_t*)(base + o_ff),
-                                                       (int*)(base + o_fl), ctl, 0, nullptr);
+    rr_multi<rr_prep_args> pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.s[0].q = q_dev;
+    pa.s[0].qbf16 = (uint16_t*)(base + o_qbf);
+    pa.s[0].qnorm = (float*)(base + o_qn);
+    pa.s[0].active = (uint8_t*)(base + o_act);
+    pa.s[0].fail_flags = (uint8_t*)(base + o_ff);
+    pa.s[0].fail_list = (int*)(base + o_fl);
+    pa.s[0].ctl = ctl;
+    pa.s[0].nq = nq;
+    pa.s[0].nq_pad = nq_pad;
+    pa.s[0].d = h->d;
+    pa.s[0].d_pad = h->d_pad;
+    rr_prep_queries_kernel<<<dim3((unsigned)nq_pad, 1), 128, 0, stream>>>(pa);
     RR_CUDA_CHECK(cudaGetLastError());
     RR_CUDA_CHECK(cudaMemsetAsync(cand_s_dev, 0xFF, (size_t)nq * capacity * sizeof(float), stream));
     RR_CUDA_CHECK(cudaMemsetAsync(cand_r_dev, 0xFF, (size_t)nq * capacity * sizeof(uint32_t), stream));
     int rc = rr_tc_scan_launch(h, (uint16_t*)(base + o_qbf), nq_pad, 0, nq, (uint8_t*)(base + o_act),
-                               &ctl->any_active, cand_s_dev, cand_r_dev, capacity, n_lists, nullptr, stream);
+                               &ctl->any_active, cand_s_dev, cand_r_dev, capacity, n_lists, nullptr, false, stream);
     if (rc != RR_OK) return rc;
     *depth = RR_TC_LIST_DEPTH;
     return RR_OK;

@@ -40,6 +40,7 @@ struct rr_index {
     int kprime = 128;
     int profile = 0;
     int scan_path = RR_PATH_AUTO;
+    int gemm_tmem_all = 1;  // <= 128 queries: whole query tile in TMEM, one accumulator stage (testing knob)
 
     // per-search scratch (grow-only)
     void* scratch = nullptr;
@@ -60,7 +61,8 @@ struct rr_index {
     int* d_nfail_total = nullptr;  // device counters (32 bytes): [0] certificate failures (int);
                                    // bytes 8..15 scanned bytes (u64); bytes 16..23 scored flops (u64)
     static constexpr int kEvPool = 4096;  // 2048 timed launches between two rr_index_get_stats calls
-    cudaEvent_t ev_pool[kEvPool] = {};
+    cudaEvent_t ev_pool[kEvPool] = {};  // pairs: [2i] before, [2i+1] after a chain of scan launches
+    int ev_launches[kEvPool / 2] = {};  // scan launches each pair brackets
     int ev_used = 0;
 };
 
@@ -94,7 +96,7 @@ struct rr_scan_counters {
 // the pass's first query) and reports the number of lists per query.
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
-                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev,
+                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev, bool chain,
                       cudaStream_t stream);
 // number of candidate lists per query the tc scan produces for this index
 int rr_tc_scan_num_lists(const rr_index* h);
@@ -116,4 +118,7 @@ int rr_gemm_scan_max_lists(const rr_index* h);
 // for which qbf16 holds ceil(nq / 256) * 256 rows.
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
                         float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
-                        const rr_collect_args* collect, cudaStream_t stream);
+                        const rr_collect_args* collect, bool chain, cudaStream_t stream);
+// `chain` (both scan launchers): this launch directly follows another scan launch on `stream`; it is
+// launched with programmatic stream serialization, i.e. its CTAs may start while the previous scan's last
+// CTAs are still running (the scans of one step touch disjoint memory), and it completes after it.

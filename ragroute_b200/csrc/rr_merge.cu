@@ -6,6 +6,8 @@
 // its strided slice, a shuffle arg-max picks the round's winner (ties: lower input
 // position), the winning lane rescans its slice.  L <= 4096 keys live in shared
 // memory; for the reference's shapes (L = S*k <= 128) that is 4 keys per lane.
+#include <algorithm>
+
 #include "rr_common.cuh"
 
 namespace {
@@ -24,29 +26,45 @@ __device__ __forceinline__ void lane_best(const uint32_t* keys, int L, int lane,
     }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-rr_merge_topk_kernel(const float* __restrict__ s, const int64_t* __restrict__ id, int64_t B, int L, int k,
-                     int descending, float* __restrict__ os, int64_t* __restrict__ oid,
-                     int32_t* __restrict__ opos) {
+// Input = n_seg segments of [B, seg_len] lists (one segment per rank after the all-gather; one segment
+// for a plain merge); entry (seg, j) of query b has input position seg * seg_len + j.
+struct MergeArgs {
+    const float* s;
+    const int64_t* id;
+    int64_t B;
+    int n_seg, seg_len;
+    int64_t seg_stride_s, seg_stride_id;  // elements between the starts of two segments
+    int k, descending;
+    int list_len;  // > 0: also decode the winner's position into (segment, list inside the segment)
+    float* os;
+    int64_t* oid;
+    int32_t* opos;
+    int32_t* osrc;
+    int32_t* orank;
+};
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(const MergeArgs a) {
     extern __shared__ uint32_t keys_all[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + w;
-    if (b >= B) return;
-    uint32_t* keys = keys_all + (size_t)w * L;
-    const float* sb = s + b * L;
-    const int64_t* ib = id + b * L;
+    if (b >= a.B) return;
+    const int L = a.n_seg * a.seg_len, k = a.k;
+    uint32_t* keys = keys_all + (size_t)w * (L + k);
+    int* wins = reinterpret_cast<int*>(keys + L);  // winner of every round
     for (int i = lane; i < L; i += 32) {
-        const float v = sb[i];
+        const int seg = i / a.seg_len, j = i - seg * a.seg_len;
+        const float v = a.s[seg * a.seg_stride_s + b * a.seg_len + j];
+        const int64_t idv = a.id[seg * a.seg_stride_id + b * a.seg_len + j];
         // order-preserving key; ascending mode ranks by -v; 0xFFFFFFFF is reserved
-        uint32_t kx = rr_float_key(descending ? v : -v);
+        uint32_t kx = rr_float_key(a.descending ? v : -v);
         if (kx == kDead) kx = kDead - 1;
-        keys[i] = (ib[i] < 0 || v != v) ? kDead : kx;
+        keys[i] = (idv < 0 || v != v) ? kDead : kx;
     }
     __syncwarp();
     uint32_t bk;
     int bp;
     lane_best(keys, L, lane, bk, bp);
-    const float pad = descending ? -3.402823466e+38f : 3.402823466e+38f;
+    int n_out = k;
     for (int r = 0; r < k; ++r) {
         // warp arg-max over (key desc, position asc)
         uint32_t wk = bk;
@@ -61,25 +79,54 @@ rr_merge_topk_kernel(const float* __restrict__ s, const int64_t* __restrict__ id
                 wp = op;
             }
         }
-        if (wp < 0) {  // fewer than k live entries: pad the rest like faiss / the oracle
-            for (int i = r + lane; i < k; i += 32) {
-                os[b * k + i] = pad;
-                oid[b * k + i] = -1;
-                if (opos) opos[b * k + i] = -1;
-            }
+        if (wp < 0) {  // fewer than k live entries
+            n_out = r;
             break;
         }
-        if (lane == 0) {
-            os[b * k + r] = sb[wp];
-            oid[b * k + r] = ib[wp];
-            if (opos) opos[b * k + r] = wp;
-        }
+        if (lane == 0) wins[r] = wp;
         if ((wp & 31) == lane) {  // owner of the winning slot retires it and rescans
             keys[wp] = kDead;
             lane_best(keys, L, lane, bk, bp);
         }
         __syncwarp();
     }
+    __syncwarp();
+    // write the winners out in parallel; pad the rest like faiss / the oracle
+    const float pad = a.descending ? -3.402823466e+38f : 3.402823466e+38f;
+    for (int r = lane; r < k; r += 32) {
+        float sv = pad;
+        int64_t iv = -1;
+        int pos = -1, src = -1, rank = -1;
+        if (r < n_out) {
+            pos = wins[r];
+            const int seg = pos / a.seg_len, j = pos - seg * a.seg_len;
+            sv = a.s[seg * a.seg_stride_s + b * a.seg_len + j];
+            iv = a.id[seg * a.seg_stride_id + b * a.seg_len + j];
+            if (a.list_len > 0) {
+                rank = seg;
+                src = j / a.list_len;
+            }
+        }
+        a.os[b * k + r] = sv;
+        a.oid[b * k + r] = iv;
+        if (a.opos) a.opos[b * k + r] = pos;
+        if (a.osrc) a.osrc[b * k + r] = src;
+        if (a.orank) a.orank[b * k + r] = rank;
+    }
+}
+
+int merge_launch(const MergeArgs& a, cudaStream_t stream) {
+    const int L = a.n_seg * a.seg_len;
+    const size_t smem = (size_t)kWarpsPerBlock * (L + a.k) * sizeof(uint32_t);
+    if (smem > (48u << 10)) {
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
+    }
+    const unsigned blocks = (unsigned)((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    rr_merge_topk_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a);
+    RR_CUDA_CHECK(cudaGetLastError());
+    rr_count_launch(1);
+    return RR_OK;
 }
 }  // namespace
 
@@ -87,18 +134,55 @@ extern "C" int rr_merge_topk(const float* s_dev, const int64_t* id_dev, int64_t 
                              int descending, float* os_dev, int64_t* oid_dev, int32_t* opos_dev,
                              void* stream) {
     RR_REQUIRE(B >= 0 && L >= 0 && k > 0, "rr_merge_topk: bad shape B=%lld L=%d k=%d", (long long)B, L, k);
-    RR_REQUIRE(L <= RR_MERGE_MAX_L, "rr_merge_topk: L=%d exceeds RR_MERGE_MAX_L=%d", L, RR_MERGE_MAX_L);
+    RR_REQUIRE(L <= RR_MERGE_MAX_L && k <= RR_MERGE_MAX_L, "rr_merge_topk: L=%d / k=%d exceeds RR_MERGE_MAX_L=%d", L, k,
+               RR_MERGE_MAX_L);
     if (B == 0) return RR_OK;
     RR_REQUIRE(os_dev && oid_dev && (L == 0 || (s_dev && id_dev)), "rr_merge_topk: NULL buffer");
-    const size_t smem = (size_t)kWarpsPerBlock * L * sizeof(uint32_t);
-    if (smem > (48u << 10)) {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-    }
-    const unsigned blocks = (unsigned)((B + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    rr_merge_topk_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-        s_dev, id_dev, B, L, k, descending, os_dev, oid_dev, opos_dev);
-    RR_CUDA_CHECK(cudaGetLastError());
-    rr_count_launch(1);
-    return RR_OK;
+    MergeArgs a = {};
+    a.s = s_dev;
+    a.id = id_dev;
+    a.B = B;
+    a.n_seg = 1;
+    a.seg_len = std::max(L, 1);
+    if (L == 0) a.n_seg = 0;
+    a.k = k;
+    a.descending = descending;
+    a.os = os_dev;
+    a.oid = oid_dev;
+    a.opos = opos_dev;
+    return merge_launch(a, (cudaStream_t)stream);
+}
+
+extern "C" int rr_merge_topk_segments(const float* s_dev, const int64_t* id_dev, int64_t B, int n_seg, int seg_len,
+                                      int64_t seg_stride_s, int64_t seg_stride_id, int k, int descending,
+                                      int list_len, float* os_dev, int64_t* oid_dev, int32_t* opos_dev,
+                                      int32_t* osrc_dev, int32_t* orank_dev, void* stream) {
+    RR_REQUIRE(B >= 0 && n_seg >= 1 && seg_len >= 1 && k > 0, "rr_merge_topk_segments: bad shape B=%lld n_seg=%d seg_len=%d k=%d",
+               (long long)B, n_seg, seg_len, k);
+    RR_REQUIRE((int64_t)n_seg * seg_len <= RR_MERGE_MAX_L && k <= RR_MERGE_MAX_L,
+               "rr_merge_topk_segments: n_seg * seg_len = %lld / k = %d exceeds RR_MERGE_MAX_L=%d",
+               (long long)n_seg * seg_len, k, RR_MERGE_MAX_L);
+    RR_REQUIRE(list_len >= 0 && (list_len == 0 || seg_len % list_len == 0),
+               "rr_merge_topk_segments: seg_len=%d is not a multiple of list_len=%d", seg_len, list_len);
+    RR_REQUIRE(n_seg == 1 || (seg_stride_s >= B * seg_len && seg_stride_id >= B * seg_len),
+               "rr_merge_topk_segments: segments overlap");
+    if (B == 0) return RR_OK;
+    RR_REQUIRE(s_dev && id_dev && os_dev && oid_dev, "rr_merge_topk_segments: NULL buffer");
+    MergeArgs a = {};
+    a.s = s_dev;
+    a.id = id_dev;
+    a.B = B;
+    a.n_seg = n_seg;
+    a.seg_len = seg_len;
+    a.seg_stride_s = seg_stride_s;
+    a.seg_stride_id = seg_stride_id;
+    a.k = k;
+    a.descending = descending;
+    a.list_len = list_len;
+    a.os = os_dev;
+    a.oid = oid_dev;
+    a.opos = opos_dev;
+    a.osrc = osrc_dev;
+    a.orank = orank_dev;
+    return merge_launch(a, (cudaStream_t)stream);
 }

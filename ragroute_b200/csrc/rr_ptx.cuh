@@ -156,6 +156,16 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
 }
 // one lane of a converged warp (warp-uniform control flow around it keeps the operands of
 // the single-thread instructions -- UTMALDG, UTCHMMA, UTCBAR -- in uniform registers)
+// Programmatic dependent launch: the scans of one step do not depend on each other, so each lets the next
+// one's CTAs start as soon as SMs free up (no launch gap, no idle SMs in the tail) and only orders its own
+// COMPLETION after its predecessor's (everything launched after the scans then sees all of them done).
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait_primary() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ bool elect_one_sync() {
     uint32_t pred;
     asm volatile(

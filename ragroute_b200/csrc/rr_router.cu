@@ -11,6 +11,7 @@
 // float64, then cast to fp32 (router.py:270-271).
 #include <math.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -19,9 +20,14 @@
 namespace {
 constexpr int kH1 = 256;
 constexpr int kH2 = 128;
-constexpr int kQB = 4;         // queries (or rows) per CTA
-constexpr int kThreads = 512;  // 2 K-halves x 256 fc1 outputs; 16 warps for the pair phase
+constexpr int kQB = 4;          // queries (or rows) per CTA
+constexpr int kThreads = 1024;  // fc1: 4 K-quarters x 256 outputs; fc2: 8 K-slices x 128 outputs
 constexpr int kWarps = kThreads / 32;
+constexpr int kKQ = kThreads / kH1;   // K-quarters of fc1
+constexpr int kKS = kThreads / kH2;   // K-slices of fc2
+constexpr int kPG = 16;               // (query, source) pairs per fc2 round
+constexpr int kHStride = kPG + 4;     // h1t row pitch: float4-aligned, spreads the transposing stores over banks
+constexpr int kInFlight = 16;         // independent weight loads per thread (the loops are L2-latency-bound)
 constexpr float kLnEps = 1e-5f;
 }  // namespace
 
@@ -75,12 +81,16 @@ struct RouterArgs {
     float* logits;            // [B][S] or null
 };
 
-__global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a) {
+// Shared memory: [ xq | part ] is dead once fc1 is done and is reused for the fc2 partial sums.
+__global__ void __launch_bounds__(kThreads, 1) rr_router_kernel(const RouterArgs a) {
     extern __shared__ __align__(16) float sm[];
-    float* xq = sm;                                 // [kQB][d_in]
-    float* part = xq + (size_t)kQB * a.d_in;        // [2][kQB][256]
-    float* g = part + 2 * kQB * kH1;                // [n_slots][kQB][256]
-    float* hbuf = g + (size_t)a.n_slots * kQB * kH1;  // [kWarps][256]
+    const size_t n_x = ((size_t)kQB * a.d_in + 3) & ~(size_t)3;
+    const size_t n_u = max(n_x + (size_t)kKQ * kQB * kH1, (size_t)kKS * kPG * kH2);
+    float* xq = sm;                                   // [kQB][d_in]
+    float* part = xq + n_x;                           // [kKQ][kQB][256]
+    float* part2 = sm;                                // [kKS][kPG][128]   (aliases xq / part)
+    float* g = sm + n_u;                              // [n_slots][kQB][256]
+    float* h1t = g + (size_t)a.n_slots * kQB * kH1;   // [256][kHStride]: relu(ln1(fc1)) of kPG pairs, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int64_t b0 = (int64_t)blockIdx.x * kQB;
@@ -88,9 +98,9 @@ __global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a)
 
     // ---- phase 1: g[slot][qb][:] = W1[:, :d_in] . scaled(x[qb][slot][:]) ----
     const int t = tid & (kH1 - 1);
-    const int half = tid >> 8;
-    const int j_lo = half ? (a.d_in >> 1) : 0;
-    const int j_hi = half ? a.d_in : (a.d_in >> 1);
+    const int kq = tid >> 8;
+    const int j_lo = (int)((int64_t)kq * a.d_in / kKQ);
+    const int j_hi = (int)((int64_t)(kq + 1) * a.d_in / kKQ);
     for (int sl = 0; sl < a.n_slots; ++sl) {
         for (int i = tid; i < kQB * a.d_in; i += kThreads) {
             const int qb = i / a.d_in, j = i - qb * a.d_in;
@@ -107,16 +117,15 @@ __global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a)
         for (int qb = 0; qb < kQB; ++qb) acc[qb] = 0.f;
         const float* wp = a.w1t + t;
         int j = j_lo;
-        // 8 independent weight loads in flight per thread: the loop is L2-latency-bound
-        for (; j + 8 <= j_hi; j += 8) {
-            float wv[8];
+        for (; j + kInFlight <= j_hi; j += kInFlight) {
+            float wv[kInFlight];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
+            for (int u = 0; u < kInFlight; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
 #pragma unroll
             for (int qb = 0; qb < kQB; ++qb) {
                 const float* xr = xq + (size_t)qb * a.d_in + j;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
+                for (int u = 0; u < kInFlight; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
             }
         }
         for (; j < j_hi; ++j) {
@@ -125,79 +134,127 @@ __global__ void __launch_bounds__(kThreads) rr_router_kernel(const RouterArgs a)
             for (int qb = 0; qb < kQB; ++qb) acc[qb] = fmaf(w0, xq[(size_t)qb * a.d_in + j], acc[qb]);
         }
 #pragma unroll
-        for (int qb = 0; qb < kQB; ++qb) part[(half * kQB + qb) * kH1 + t] = acc[qb];
+        for (int qb = 0; qb < kQB; ++qb) part[(kq * kQB + qb) * kH1 + t] = acc[qb];
         __syncthreads();
-        for (int i = tid; i < kQB * kH1; i += kThreads)
-            g[(size_t)sl * kQB * kH1 + i] = part[i] + part[kQB * kH1 + i];
+        for (int i = tid; i < kQB * kH1; i += kThreads) {
+            float v = part[i];
+#pragma unroll
+            for (int c = 1; c < kKQ; ++c) v += part[c * kQB * kH1 + i];
+            g[(size_t)sl * kQB * kH1 + i] = v;
+        }
         __syncthreads();
     }
 
-    // ---- phase 2: one warp per (query, source) pair ----
-    float* hw = hbuf + w * kH1;
+    // ---- phase 2: (query, source) pairs, kPG at a time ----
     const int n_pairs = nqb * a.S;
-    for (int pi = w; pi < n_pairs; pi += kWarps) {
-        const int qb = pi / a.S, s = pi - qb * a.S;
-        const int sl = a.slot_of_source ? a.slot_of_source[s] : 0;
-        const float* gp = g + ((size_t)sl * kQB + qb) * kH1;
-        const float* cp = a.c1 + (size_t)s * kH1;
-        float h[8];
-        float sum = 0.f;
+    const int o2 = tid & (kH2 - 1);
+    const int ks = tid >> 7;
+    for (int p0 = 0; p0 < n_pairs; p0 += kPG) {
+        const int np = min(kPG, n_pairs - p0);
+        // (a) one warp per pair: h = relu(ln1(g + c1_s)), stored transposed for the fc2 threads
+        if (w < kPG) {
+            const int pi = p0 + w;
+            float h[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int i = lane + 32 * c;
-            h[c] = gp[i] + cp[i];
-            sum += h[c];
+            for (int c = 0; c < 8; ++c) h[c] = 0.f;
+            if (w < np) {
+                const int qb = pi / a.S, s = pi - qb * a.S;
+                const int sl = a.slot_of_source ? a.slot_of_source[s] : 0;
+                const float* gp = g + ((size_t)sl * kQB + qb) * kH1;
+                const float* cp = a.c1 + (size_t)s * kH1;
+                float sum = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int i = lane + 32 * c;
+                    h[c] = gp[i] + cp[i];
+                    sum += h[c];
+                }
+                const float mean1 = rr_warp_sum(sum) * (1.0f / kH1);
+                float var = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float dlt = h[c] - mean1;
+                    var = fmaf(dlt, dlt, var);
+                }
+                const float rstd1 = 1.0f / sqrtf(rr_warp_sum(var) * (1.0f / kH1) + kLnEps);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int i = lane + 32 * c;
+                    h[c] = fmaxf((h[c] - mean1) * rstd1 * a.ln1w[i] + a.ln1b[i], 0.f);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 8; ++c) h1t[(lane + 32 * c) * kHStride + w] = h[c];
         }
-        const float mean1 = rr_warp_sum(sum) * (1.0f / kH1);
-        float var = 0.f;
+        __syncthreads();
+        // (b) fc2 partial sums: thread = (output o2, K-slice ks), all kPG pairs at once
+        {
+            float acc[kPG];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const float dlt = h[c] - mean1;
-            var = fmaf(dlt, dlt, var);
+            for (int p = 0; p < kPG; ++p) acc[p] = 0.f;
+            constexpr int kPer = kH1 / kKS;  // 32 inputs per slice
+            const float* wr = a.w2t + (size_t)(ks * kPer) * kH2 + o2;
+#pragma unroll
+            for (int i0 = 0; i0 < kPer; i0 += kInFlight) {
+                float wv[kInFlight];
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) wv[u] = __ldg(wr + (size_t)(i0 + u) * kH2);
+#pragma unroll
+                for (int u = 0; u < kInFlight; ++u) {
+                    const float4* hp = reinterpret_cast<const float4*>(h1t + (size_t)(ks * kPer + i0 + u) * kHStride);
+#pragma unroll
+                    for (int p4 = 0; p4 < kPG / 4; ++p4) {
+                        const float4 hv = hp[p4];
+                        acc[4 * p4 + 0] = fmaf(wv[u], hv.x, acc[4 * p4 + 0]);
+                        acc[4 * p4 + 1] = fmaf(wv[u], hv.y, acc[4 * p4 + 1]);
+                        acc[4 * p4 + 2] = fmaf(wv[u], hv.z, acc[4 * p4 + 2]);
+                        acc[4 * p4 + 3] = fmaf(wv[u], hv.w, acc[4 * p4 + 3]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int p = 0; p < kPG; ++p) part2[((size_t)ks * kPG + p) * kH2 + o2] = acc[p];
         }
-        const float rstd1 = 1.0f / sqrtf(rr_warp_sum(var) * (1.0f / kH1) + kLnEps);
+        __syncthreads();
+        // (c) one warp per pair: fold the K-slices, ln2, relu, fc3, sigmoid, threshold
+        if (w < np) {
+            const int pi = p0 + w;
+            const int qb = pi / a.S, s = pi - qb * a.S;
+            float o[4];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int i = lane + 32 * c;
-            const float y = (h[c] - mean1) * rstd1 * a.ln1w[i] + a.ln1b[i];
-            hw[i] = fmaxf(y, 0.f);
-        }
-        __syncwarp();
-        float o[4];
+            for (int c = 0; c < 4; ++c) {
+                float v = a.b2[lane + 32 * c];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) o[c] = a.b2[lane + 32 * c];
-        for (int i = 0; i < kH1; ++i) {
-            const float hv = hw[i];
-            const float* wr = a.w2t + (size_t)i * kH2 + lane;
+                for (int k2 = 0; k2 < kKS; ++k2) v += part2[((size_t)k2 * kPG + w) * kH2 + lane + 32 * c];
+                o[c] = v;
+            }
+            const float sum2 = o[0] + o[1] + o[2] + o[3];
+            const float mean2 = rr_warp_sum(sum2) * (1.0f / kH2);
+            float var2 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 4; ++c) o[c] = fmaf(__ldg(wr + 32 * c), hv, o[c]);
-        }
-        float sum2 = o[0] + o[1] + o[2] + o[3];
-        const float mean2 = rr_warp_sum(sum2) * (1.0f / kH2);
-        float var2 = 0.f;
+            for (int c = 0; c < 4; ++c) {
+                const float dlt = o[c] - mean2;
+                var2 = fmaf(dlt, dlt, var2);
+            }
+            const float rstd2 = 1.0f / sqrtf(rr_warp_sum(var2) * (1.0f / kH2) + kLnEps);
+            float dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const float dlt = o[c] - mean2;
-            var2 = fmaf(dlt, dlt, var2);
-        }
-        const float rstd2 = 1.0f / sqrtf(rr_warp_sum(var2) * (1.0f / kH2) + kLnEps);
-        float dot = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int i = lane + 32 * c;
-            const float y = fmaxf((o[c] - mean2) * rstd2 * a.ln2w[i] + a.ln2b[i], 0.f);
-            dot = fmaf(a.w3[i], y, dot);
-        }
-        const float logit = rr_warp_sum(dot) + a.b3[0];
-        if (lane == 0) {
-            const int64_t oidx = (b0 + qb) * a.S + s;
-            if (a.logits) a.logits[oidx] = logit;
-            if (a.mask) {
-                const float prob = 1.0f / (1.0f + expf(-logit));  // torch.sigmoid, router.py:276
-                a.mask[oidx] = prob > a.prob_thr ? 1 : 0;          // strict, router.py:278-280
+            for (int c = 0; c < 4; ++c) {
+                const int i = lane + 32 * c;
+                const float y = fmaxf((o[c] - mean2) * rstd2 * a.ln2w[i] + a.ln2b[i], 0.f);
+                dot = fmaf(a.w3[i], y, dot);
+            }
+            const float logit = rr_warp_sum(dot) + a.b3[0];
+            if (lane == 0) {
+                const int64_t oidx = (b0 + qb) * a.S + s;
+                if (a.logits) a.logits[oidx] = logit;
+                if (a.mask) {
+                    const float prob = 1.0f / (1.0f + expf(-logit));  // torch.sigmoid, router.py:276
+                    a.mask[oidx] = prob > a.prob_thr ? 1 : 0;          // strict, router.py:278-280
+                }
             }
         }
-        __syncwarp();
+        __syncthreads();  // h1t / part2 are rewritten by the next round
     }
 }
 
@@ -209,8 +266,9 @@ int upload(T** dst, const T* src, size_t n) {
 }
 
 size_t router_smem(int d_in, int n_slots) {
-    return ((size_t)kQB * d_in + 2 * kQB * kH1 + (size_t)n_slots * kQB * kH1 + (size_t)kWarps * kH1) *
-           sizeof(float);
+    const size_t n_x = ((size_t)kQB * d_in + 3) & ~(size_t)3;
+    const size_t n_u = std::max(n_x + (size_t)kKQ * kQB * kH1, (size_t)kKS * kPG * kH2);
+    return (n_u + (size_t)n_slots * kQB * kH1 + (size_t)kH1 * kHStride) * sizeof(float);
 }
 
 int router_launch(rr_router* h, const RouterArgs& a, cudaStream_t stream) {

@@ -137,8 +137,12 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     const GemmParams p) {
     // Work split, decided on the device from the number of ROUTED queries: nqt query tiles of
     // 128 * CG (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
+    pdl_launch_dependents();  // the next scan of the step may take SMs as they free up
     const int n_active = p.ctl->n_active;
-    if (n_active == 0) return;  // no query routed to this source: do not touch the corpus
+    if (n_active == 0) {  // no query routed to this source: do not touch the corpus
+        pdl_wait_primary();
+        return;
+    }
     const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;  // 0 = leader (issues the MMAs)
     const int unit = (int)blockIdx.x / CG;                       // work unit = CTA or CTA pair
     const int n_units = (int)gridDim.x / CG;
@@ -154,7 +158,10 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                       2ull * (unsigned long long)n_active * (unsigned long long)p.n_rows * (unsigned long long)p.d_pad);
         }
     }
-    if (slice >= n_slices) return;  // leftover CTAs (gridDim.x is not a multiple of nqt)
+    if (slice >= n_slices) {  // leftover CTAs (gridDim.x is not a multiple of nqt)
+        pdl_wait_primary();
+        return;
+    }
     const uint64_t l2_hint = (nqt > 1) ? p.l2_hint_shared : p.l2_hint;
     // corpus rows / bytes of THIS CTA per tile chunk: all 128 rows (16 KB) or, in a pair, its 64 (8 KB)
     constexpr int kRowsCta = kNT / CG;
@@ -351,18 +358,26 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int qg = qt * kQTile + t;      // query inside the chunk
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         {
-            // each thread copies its own query row (a_cols * 4 bytes) into its TMEM lane; 8 x 16-byte
-            // loads in flight per thread (a_cols is a multiple of 32: whole K-chunks)
+            // each thread copies its own query row (a_cols * 4 bytes) into its TMEM lane; 16 x 16-byte
+            // loads in flight per thread (a_cols is a multiple of 32: whole K-chunks) -- nothing streams
+            // until the tile is in place, so this latency is paid once per launch by the whole SM
             const uint4* src = reinterpret_cast<const uint4*>(p.qbf16 + (size_t)qg * p.d_pad);
-            for (uint32_t c = 0; c < a_cols; c += 32) {
-                uint4 v[8];
+            for (uint32_t c = 0; c < a_cols; c += 64) {
+                uint4 v[16];
+                const bool two = c + 32 < a_cols;
 #pragma unroll
                 for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (c >> 2) + u);
+                if (two) {
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint32_t r[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                           v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
-                    tmem_st_x8(lane_addr + c + 8 * u, r);
+                    for (int u = 8; u < 16; ++u) v[u] = __ldg(src + (c >> 2) + u);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (u < 4 || two) {
+                        const uint32_t r[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
+                                               v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                        tmem_st_x8(lane_addr + c + 8 * u, r);
+                    }
                 }
             }
             tmem_st_wait();
@@ -482,6 +497,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (CG == 2) tmem_dealloc_2cta(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
+    pdl_wait_primary();  // complete only after the previous scan of the chain has
 }
 
 }  // namespace
@@ -494,7 +510,8 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
 template <int CG, bool COLLECT>
-static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, cudaStream_t stream) {
+static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, bool chain,
+                     cudaStream_t stream) {
     const size_t stage_b = (size_t)kStageBytes / CG;
     const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
                          (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
@@ -512,20 +529,22 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = chain ? 2 : 1;
     RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT>, tx, tq, p));
     return RR_OK;
 }
 
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
                         float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
-                        const rr_collect_args* collect, cudaStream_t stream) {
+                        const rr_collect_args* collect, bool chain, cudaStream_t stream) {
     RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
     RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
     RR_REQUIRE(cta_group == 1 || cta_group == 2, "rr_gemm_scan_launch: cta_group must be 1 or 2");
@@ -550,6 +569,15 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
     p.acc_stages = kMaxAcc;
     p.a_tmem_kc = std::min(p.num_kc, kMaxATmemKc);
     p.a_smem_kc = p.num_kc - p.a_tmem_kc;
+    if (nq <= kQTile && cta_group == 1 && h->gemm_tmem_all && p.num_kc * 32 + kNT <= (int)kTmemCols) {
+        // one query tile = the HBM-bound regime (intensity <= 128 flop/byte): the tensor pipe has slack, so the
+        // whole tile goes to TMEM with ONE accumulator stage (the MMAs of the next corpus tile wait for the
+        // epilogue's tcgen05.ld, a fraction of the tile's HBM time) and the shared memory it frees becomes
+        // two more TMA stages in flight
+        p.a_tmem_kc = p.num_kc;
+        p.a_smem_kc = 0;
+        p.acc_stages = 1;
+    }
     p.stages = 0;
     // sibling units (other query tiles, same slice) re-read each tile from L2 right away
     p.l2_hint = kTmaEvictFirst;
@@ -572,8 +600,8 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
     int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, nq_rows, h->d_pad, kQTile);
     if (rc != RR_OK) return rc;
     if (collect)
-        return cta_group == 2 ? launch_cg<2, true>(h, h->tmap_hi64, tq, p, stream)
-                              : launch_cg<1, true>(h, h->tmap_hi, tq, p, stream);
-    return cta_group == 2 ? launch_cg<2, false>(h, h->tmap_hi64, tq, p, stream)
-                          : launch_cg<1, false>(h, h->tmap_hi, tq, p, stream);
+        return cta_group == 2 ? launch_cg<2, true>(h, h->tmap_hi64, tq, p, chain, stream)
+                              : launch_cg<1, true>(h, h->tmap_hi, tq, p, chain, stream);
+    return cta_group == 2 ? launch_cg<2, false>(h, h->tmap_hi64, tq, p, chain, stream)
+                          : launch_cg<1, false>(h, h->tmap_hi, tq, p, chain, stream);
 }

@@ -92,7 +92,11 @@ template <int QT>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                   const TcParams p) {
-    if (*p.any_active == 0) return;  // no query routed to this source: do not touch the corpus
+    pdl_launch_dependents();  // the next scan of the step may take SMs as they free up
+    if (*p.any_active == 0) {  // no query routed to this source: do not touch the corpus
+        pdl_wait_primary();
+        return;
+    }
     if (p.counters && blockIdx.x == 0 && threadIdx.x == 0) {
         int n_act = 0;
         for (int q = 0; q < p.nq_tile; ++q) n_act += p.active[q] ? 1 : 0;
@@ -285,6 +289,7 @@ rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         tc_fence_after();
         tmem_dealloc(tmem_base, kTmemCols);
     }
+    pdl_wait_primary();  // complete only after the previous scan of the chain has
 }
 
 // ------------------------------------------------------------------ host ----
@@ -307,7 +312,7 @@ SmemPlan plan_smem(int d_pad, int qt) {
 }
 
 template <int QT>
-int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem,
+int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem, bool chain,
               cudaStream_t stream) {
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
@@ -315,8 +320,17 @@ int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, s
                                            kSmemLimit));
         attr_done[h->device & 63] = true;
     }
-    rr_tc_scan_kernel<QT><<<grid, kThreads, smem, stream>>>(h->tmap_hi, tq, p);
-    RR_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = chain ? 1 : 0;
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_tc_scan_kernel<QT>, h->tmap_hi, tq, p));
     return RR_OK;
 }
 
@@ -333,7 +347,7 @@ int rr_tc_scan_num_lists(const rr_index* h) { return h->sm_count * RR_TC_EPI_WAR
 
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
-                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev,
+                      int64_t cand_stride, int* n_lists_out, rr_scan_counters* counters_dev, bool chain,
                       cudaStream_t stream) {
     const int qt = rr_tc_scan_qtile(h);
     RR_REQUIRE(qt > 0 && nq_tile >= 1 && nq_tile <= qt, "rr_tc_scan_launch: bad query tile");
@@ -365,8 +379,8 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
     const int grid = std::min(h->sm_count, p.n_tiles);
     *n_lists_out = grid * RR_TC_EPI_WARPS;
     switch (qt) {
-        case 64: return launch_qt<64>(h, tq, p, grid, pl.bytes, stream);
-        case 32: return launch_qt<32>(h, tq, p, grid, pl.bytes, stream);
-        default: return launch_qt<16>(h, tq, p, grid, pl.bytes, stream);
+        case 64: return launch_qt<64>(h, tq, p, grid, pl.bytes, chain, stream);
+        case 32: return launch_qt<32>(h, tq, p, grid, pl.bytes, chain, stream);
+        default: return launch_qt<16>(h, tq, p, grid, pl.bytes, chain, stream);
     }
 }

@@ -21,6 +21,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
+from . import _lib
+from .faiss_compat import IndexFlatIP
 from .rerank import merge_topk
 from .router import DEFAULT_THRESHOLD, FusedCorpusRouter
 
@@ -68,13 +70,59 @@ def decode_pos(pos: torch.Tensor, n_sources: int, k: int) -> Tuple[torch.Tensor,
     return rank, src
 
 
+class PackedLists:
+    """Per-source lists of one rank as ONE byte block: [scores fp32 [B, L] | ids int64 [B, L]], each part
+    padded to 16 bytes.  The search writes straight into the views, the block travels in one all-gather,
+    and the merge kernel reads the gathered blocks in place (rr_merge_topk_segments) -- no packing or
+    unpacking copies on the step."""
+
+    def __init__(self, B: int, L: int, device, n_blocks: int = 1):
+        self.B, self.L, self.n_blocks = B, L, n_blocks
+        self.n_scores = -(-(B * L * 4) // 16) * 16
+        self.block_bytes = self.n_scores + -(-(B * L * 8) // 16) * 16
+        self.buf = torch.empty(n_blocks * self.block_bytes, dtype=torch.uint8, device=device)
+
+    def scores(self, block: int = 0) -> torch.Tensor:
+        o = block * self.block_bytes
+        return self.buf[o:o + self.B * self.L * 4].view(torch.float32).view(self.B, self.L)
+
+    def ids(self, block: int = 0) -> torch.Tensor:
+        o = block * self.block_bytes + self.n_scores
+        return self.buf[o:o + self.B * self.L * 8].view(torch.int64).view(self.B, self.L)
+
+    def gather(self, group=None) -> "PackedLists":
+        """All ranks' blocks, rank-major (one collective)."""
+        import torch.distributed as dist
+        W = dist.get_world_size(group)
+        out = PackedLists(self.B, self.L, self.buf.device, n_blocks=W)
+        dist.all_gather_into_tensor(out.buf, self.buf, group=group)
+        return out
+
+
+def merge_packed(lists: PackedLists, k: int, list_len: int, descending: bool = True):
+    """Merge every block of `lists` ([B, n_blocks * L] in block-major order) on the GPU.
+    Returns (scores [B,k], ids [B,k], pos, source, rank int32 [B,k])."""
+    B, dev = lists.B, lists.buf.device
+    with torch.cuda.device(dev):
+        os_ = torch.empty((B, k), dtype=torch.float32, device=dev)
+        oi = torch.empty((B, k), dtype=torch.int64, device=dev)
+        meta = torch.empty((3, B, k), dtype=torch.int32, device=dev)
+        base = lists.buf.data_ptr()
+        _lib.check(_lib.load().rr_merge_topk_segments(
+            base, base + lists.n_scores, B, lists.n_blocks, lists.L, lists.block_bytes // 4, lists.block_bytes // 8,
+            int(k), 1 if descending else 0, int(list_len), os_.data_ptr(), oi.data_ptr(), meta[0].data_ptr(),
+            meta[1].data_ptr(), meta[2].data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return os_, oi, meta[0], meta[1], meta[2]
+
+
 class Federation:
     """A set of named sources (IndexFlatIP-shaped objects on one GPU, each possibly a
     row shard), an optional router, and the merge."""
 
     def __init__(self, sources: Dict[str, object], k: int, router: Optional[FusedCorpusRouter] = None,
                  routing: str = "ragroute", threshold: float = DEFAULT_THRESHOLD, descending: bool = True,
-                 dataset: str = "medrag", group=None, distributed: bool = False, seed: int = 0):
+                 dataset: str = "medrag", group=None, distributed: bool = False, seed: int = 0,
+                 fused: bool = True):
         if routing not in ROUTING_STRATEGIES:
             raise ValueError(f"Unknown routing strategy: {routing}")  # router.py:239
         if routing == "ragroute" and router is None:
@@ -89,6 +137,8 @@ class Federation:
         self.dataset = dataset
         self.group = group
         self.distributed = distributed
+        self.fused = fused  # False: one rr_index_search_ex call per source (testing)
+        self._packed: Optional[PackedLists] = None
         self._rng = random.Random(seed)
         if router is not None and routing == "ragroute":
             assert list(router.data_sources) == self.names, "router and federation must list sources in the same order"
@@ -125,21 +175,38 @@ class Federation:
         S, k = len(self.names), self.k
         q0 = q[0] if isinstance(q, (list, tuple)) else q
         B = q0.shape[0]
-        D_loc = torch.empty((B, S * k), dtype=torch.float32, device=q0.device)
-        I_loc = torch.empty((B, S * k), dtype=torch.int64, device=q0.device)
+        self._packed = PackedLists(B, S * k, q0.device)
+        D_loc, I_loc = self._packed.scores(), self._packed.ids()
+        qs_list = [(q[s] if isinstance(q, (list, tuple)) else q) for s in range(S)]
+        if self.fused and all(isinstance(ix, IndexFlatIP) for ix in self.indexes):
+            # one native call for the whole fan-out (http_server.py:200-209): one scan launch per source,
+            # every other stage batched over the sources
+            for ix, qs in zip(self.indexes, qs_list):
+                assert qs.is_cuda and qs.dtype == torch.float32 and qs.is_contiguous() and qs.shape == (B, ix.d)
+                assert ix.device == qs.device.index, "source and queries on different devices"
+            if mask is not None:
+                assert mask.is_cuda and mask.dtype == torch.uint8 and mask.is_contiguous() and mask.shape == (B, S)
+            handles = (_lib.c_void_p * S)(*[ix._h for ix in self.indexes])
+            qptrs = (_lib.c_void_p * S)(*[qs.data_ptr() for qs in qs_list])
+            with torch.cuda.device(q0.device):
+                _lib.check(_lib.load().rr_federation_search(
+                    handles, S, qptrs, B, int(k), None if mask is None else mask.data_ptr(), S,
+                    D_loc.data_ptr(), I_loc.data_ptr(), S * k, torch.cuda.current_stream().cuda_stream))
+            return D_loc, I_loc
         for s, index in enumerate(self.indexes):
-            qs = q[s] if isinstance(q, (list, tuple)) else q
-            index.search_tensor(qs, k, mask=mask, mask_col=s, out=(D_loc, I_loc), out_col=s * k)
+            index.search_tensor(qs_list[s], k, mask=mask, mask_col=s, out=(D_loc, I_loc), out_col=s * k)
         return D_loc, I_loc
 
     def merge(self, D_loc: torch.Tensor, I_loc: torch.Tensor, mask: Optional[torch.Tensor] = None):
         S, k = len(self.names), self.k
+        packed = getattr(self, "_packed", None)
+        if packed is None or packed.scores().data_ptr() != D_loc.data_ptr() or packed.ids().data_ptr() != I_loc.data_ptr():
+            packed = PackedLists(D_loc.shape[0], S * k, D_loc.device)   # lists that did not come from search_sources
+            packed.scores().copy_(D_loc)
+            packed.ids().copy_(I_loc)
         if self.distributed:
-            D_cat, I_cat = gather_lists(D_loc, I_loc, self.group)
-        else:
-            D_cat, I_cat = D_loc, I_loc
-        scores, ids, pos = merge_topk(D_cat, I_cat, k, descending=self.descending)
-        rank, src = decode_pos(pos, S, k)
+            packed = packed.gather(self.group)
+        scores, ids, _, src, rank = merge_packed(packed, k, k, descending=self.descending)
         return {"scores": scores, "ids": ids, "source": src, "rank": rank, "mask": mask}
 
     # -- host-buffer entry point (what a server process calls) --------------------------

@@ -214,3 +214,74 @@ def test_micro_batcher_over_a_real_index(cuda_required):
     for i, (D, I) in enumerate(res):
         D1, I1 = ix.search(qs[i:i + 1], k)
         assert np.array_equal(I, I1) and np.array_equal(D, D1)
+
+
+@pytest.mark.parametrize("B", [1, 7, 64, 100, 300, 2100])
+def test_fused_fan_out_equals_per_source_calls(cuda_required, B):
+    """rr_federation_search (one launch per stage for all sources) returns bit for bit what one
+    rr_index_search_ex per source returns, on every dispatch path (swap-AB scan, queries-in-TMEM scan,
+    CTA pairs, two chunks), with a routing mask, an empty source, an exact-mode source and a source
+    whose near-duplicate rows force the second pass."""
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation
+    d, k = 768, 32
+    rng = np.random.default_rng(B)
+    corpora = [syn.corpus_rows(0, 9000, d), syn.corpus_rows(1, 4100, d), np.zeros((0, d), np.float32),
+               syn.corpus_rows(2, 2500, d)]
+    base = syn.corpus_rows(3, 12, d)
+    dup = np.repeat(base, 200, axis=0) * (1 + 1e-4 * rng.standard_normal((2400, 1)).astype(np.float32))
+    corpora.append(dup.astype(np.float32))                       # 200 near-copies of each row: certificates fail
+    sources = {}
+    for i, xb in enumerate(corpora):
+        ix = IndexFlatIP(d)
+        if len(xb):
+            ix.add(xb)
+        ix.set_id_offset(1000 * i)
+        if i == 3:
+            ix.set_mode("exact")
+        sources[f"s{i}"] = ix
+    q = torch.from_numpy(syn.queries(B, d, [0, 1, 2, 3], seed=100 + B)).cuda()
+    mask = torch.from_numpy((rng.random((B, len(corpora))) < 0.6).astype(np.uint8)).cuda()
+    res = {}
+    for fused in (True, False):
+        fed = Federation(sources, k, routing="all", fused=fused)
+        D, I = fed.search_sources(q, mask)
+        torch.cuda.synchronize()
+        res[fused] = (D.clone(), I.clone())
+    assert torch.equal(res[True][1], res[False][1])
+    assert torch.equal(res[True][0], res[False][0])
+    m = mask.cpu().numpy().astype(bool)
+    I = res[True][1].cpu().numpy().reshape(B, len(corpora), k)
+    assert (I[~m] == -1).all() and (I[:, 2] == -1).all()
+    assert (I[m[:, 0], 0] >= 0).all() and (I[m[:, 4], 4] >= 4000).all()
+    if B >= 7:
+        assert sources["s4"].stats()["exact_rescans"] > 0          # the second pass really ran
+    # unmasked call (mask NULL) through the same entry point
+    fed = Federation(sources, k, routing="all", fused=True)
+    D1, I1 = fed.search_sources(q, None)
+    fed2 = Federation(sources, k, routing="all", fused=False)
+    D2, I2 = fed2.search_sources(q, None)
+    torch.cuda.synchronize()
+    assert torch.equal(I1, I2) and torch.equal(D1, D2)
+
+
+def test_fused_fan_out_rejects_bad_arguments(cuda_required):
+    from ragroute_b200 import _lib
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    lib = _lib.load()
+    ix = IndexFlatIP(64)
+    ix.add(np.ones((10, 64), np.float32))
+    q = torch.ones((2, 64), device="cuda")
+    D = torch.empty((2, 64), device="cuda")
+    I = torch.empty((2, 64), dtype=torch.int64, device="cuda")
+    hs = (_lib.c_void_p * 2)(ix._h, ix._h)
+    qs = (_lib.c_void_p * 2)(q.data_ptr(), q.data_ptr())
+    rc = lib.rr_federation_search(hs, 2, qs, 2, 32, None, 0, D.data_ptr(), I.data_ptr(), 0, None)
+    assert rc == -1 and b"twice" in lib.rr_last_error()
+    rc = lib.rr_federation_search(hs, 1, qs, 2, 33, None, 0, D.data_ptr(), I.data_ptr(), 0, None)
+    assert rc == -4
+    rc = lib.rr_federation_search(hs, 1, qs, 2, 32, None, 0, D.data_ptr(), I.data_ptr(), 16, None)
+    assert rc == -1
+    rc = lib.rr_federation_search(hs, 0, qs, 2, 32, None, 0, D.data_ptr(), I.data_ptr(), 0, None)
+    assert rc == -1

@@ -108,6 +108,48 @@ def test_merge_topk_vs_oracle_with_ties_and_holes(cuda_required, B, L, k, descen
     assert np.array_equal(p.cpu().numpy(), rp)
 
 
+@pytest.mark.parametrize("B,W,S,k", [(1, 1, 4, 32), (9, 2, 4, 32), (64, 8, 4, 32), (5, 3, 13, 10), (130, 4, 1, 32)])
+@pytest.mark.parametrize("descending", [True, False])
+def test_merge_segments_in_place_vs_oracle(cuda_required, B, W, S, k, descending):
+    """rr_merge_topk_segments over W gathered blocks (the all-gather's receive buffer, read in place)
+    equals the oracle's merge over their concatenation; source / rank are decoded on the device."""
+    from ragroute_b200.federation import PackedLists, merge_packed, decode_pos
+    rng = np.random.default_rng(B * 100 + W * 10 + S)
+    L = S * k
+    scores = rng.integers(0, 60, size=(W, B, L)).astype(np.float32) / 4   # many exact ties
+    ids = rng.integers(0, 1 << 40, size=(W, B, L)).astype(np.int64)
+    ids[rng.random((W, B, L)) < 0.3] = -1
+    scores[ids < 0] = -np.finfo(np.float32).max if descending else np.finfo(np.float32).max
+    pl = PackedLists(B, L, "cuda", n_blocks=W)
+    pl.buf.fill_(0xAB)
+    for r in range(W):
+        pl.scores(r).copy_(torch.from_numpy(scores[r]))
+        pl.ids(r).copy_(torch.from_numpy(ids[r]))
+    s, i, pos, src, rank = merge_packed(pl, k, k, descending)
+    cat_s = np.concatenate(list(scores), axis=1)
+    cat_i = np.concatenate(list(ids), axis=1)
+    rs, ri, rp = rerank_ref.merge_topk(cat_s, cat_i, k, descending)
+    assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(i.cpu().numpy(), ri)
+    assert np.array_equal(pos.cpu().numpy(), rp)
+    r_ref, s_ref = decode_pos(torch.from_numpy(rp), S, k)
+    assert np.array_equal(rank.cpu().numpy(), r_ref.numpy()) and np.array_equal(src.cpu().numpy(), s_ref.numpy())
+
+
+def test_merge_segments_rejects_bad_arguments(cuda_required):
+    from ragroute_b200 import _lib
+    lib = _lib.load()
+    z = torch.zeros(4096, device="cuda")
+    zi = torch.zeros(4096, dtype=torch.int64, device="cuda")
+    args = lambda n_seg, seg_len, ss, si, k, ll: (z.data_ptr(), zi.data_ptr(), 2, n_seg, seg_len, ss, si, k, 1, ll,
+                                                  z.data_ptr(), zi.data_ptr(), None, None, None, None)
+    assert lib.rr_merge_topk_segments(*args(2, 64, 128, 128, 32, 32)) == 0
+    assert lib.rr_merge_topk_segments(*args(2, 64, 100, 128, 32, 32)) == -1     # overlapping segments
+    assert lib.rr_merge_topk_segments(*args(2, 64, 128, 128, 32, 48)) == -1     # seg_len % list_len
+    assert lib.rr_merge_topk_segments(*args(80, 64, 128, 128, 32, 32)) == -1    # > RR_MERGE_MAX_L
+    assert lib.rr_merge_topk_segments(*args(0, 64, 128, 128, 32, 32)) == -1
+    torch.cuda.synchronize()
+
+
 def test_load_router_from_reference_style_artifacts(cuda_required, tmp_path):
     """best_model.pth + preprocessed_data.pkl + *_stats.json, laid out as Router.load_router reads them
     (router.py:106-151), loaded through ragroute_b200.artifacts and checked against the oracle."""

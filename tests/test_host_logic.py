@@ -68,7 +68,7 @@ _WORKER = r"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, {repo!r})
-from ragroute_b200.federation import gather_lists, decode_pos, shard_rows
+from ragroute_b200.federation import gather_lists, decode_pos, shard_rows, PackedLists
 from ragroute_b200 import synthetic as syn
 from oracle import flat_ip, rerank_ref
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
@@ -83,6 +83,13 @@ for s in range(S):
     D_loc[:, s*k:(s+1)*k] = Ds; I_loc[:, s*k:(s+1)*k] = np.where(Is >= 0, Is + lo, -1)
 D_cat, I_cat = gather_lists(torch.from_numpy(D_loc), torch.from_numpy(I_loc))
 assert D_cat.shape == (B, W * S * k)
+# the packed block the GPU path sends (one collective, merge kernel reads the blocks in place)
+pl = PackedLists(B, S * k, "cpu")
+pl.scores().copy_(torch.from_numpy(D_loc)); pl.ids().copy_(torch.from_numpy(I_loc))
+g = pl.gather()
+assert g.n_blocks == W and g.block_bytes % 16 == 0 and g.n_scores % 16 == 0
+assert torch.equal(torch.cat([g.scores(r) for r in range(W)], dim=1), D_cat)
+assert torch.equal(torch.cat([g.ids(r) for r in range(W)], dim=1), I_cat)
 ms, mi, mp = rerank_ref.merge_topk(D_cat.numpy(), I_cat.numpy(), k)
 r, src = decode_pos(torch.from_numpy(mp), S, k)
 # unsharded truth
