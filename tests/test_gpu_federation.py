@@ -285,3 +285,96 @@ def test_fused_fan_out_rejects_bad_arguments(cuda_required):
     assert rc == -1
     rc = lib.rr_federation_search(hs, 0, qs, 2, 32, None, 0, D.data_ptr(), I.data_ptr(), 0, None)
     assert rc == -1
+
+
+def test_config5_sixteen_mixed_dim_sources_placed_on_two_ranks(cuda_required):
+    """BASELINE config 5: 16 sources, dims cycling 384 / 768 / 1024, k = 10, no scaler,
+    in_dim = 2*1024 + 16, 64 queries in flight (--parallel 64).  (a) routed per-source top-10 and the
+    router mask against the oracle; (b) whole-source placement over 2 ranks (each rank holds every other
+    source and an empty index for the rest), the ranks' packed lists merged as the all-gather would
+    deliver them, equals the single-process result."""
+    from oracle import flat_ip, router_ref
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation, PackedLists, merge_packed, place_sources
+    from ragroute_b200.router import FusedCorpusRouter
+    S, k, B, d_max = 16, 10, 64, 1024
+    dims = [(384, 768, 1024)[i % 3] for i in range(S)]
+    names = [f"src{i:02d}" for i in range(S)]
+    model = {n: f"enc{dims[i]}" for i, n in enumerate(names)}
+    rng = np.random.default_rng(55)
+    n_rows = np.exp(rng.uniform(np.log(500), np.log(20000), size=S)).astype(int)   # log-uniform sizes, scaled down
+    corpora, centroids = {}, {}
+    for i, n in enumerate(names):
+        d = dims[i]
+        mu = rng.standard_normal(d).astype(np.float32) * np.float32(0.5 / np.sqrt(d))
+        corpora[n] = rng.standard_normal((n_rows[i], d), dtype=np.float32) / np.float32(np.sqrt(d)) + mu
+        centroids[n] = np.pad(corpora[n].mean(axis=0), (0, d_max - d)).astype(np.float32)
+    q_by_model = {f"enc{d}": rng.standard_normal((B, d), dtype=np.float32) / np.float32(np.sqrt(d))
+                  for d in (384, 768, 1024)}
+    in_dim = 2 * d_max + S
+    sd = syn.router_state_dict(in_dim, 9)
+    onehot = {n: i for i, n in enumerate(names)}
+
+    def make_router(sd_):
+        r = FusedCorpusRouter(in_dim)
+        r.load_state_dict(sd_)
+        r.set_tables(names, d_max, model, centroids, onehot, S, scaler=None)
+        return r
+
+    router = make_router(sd)
+    q_router = np.zeros((B, len(router.slot_names), d_max), dtype=np.float32)
+    for si, m in enumerate(router.slot_names):
+        q_router[:, si, :q_by_model[m].shape[1]] = q_by_model[m]
+    qr = torch.from_numpy(q_router).cuda()
+    _, lg = router.select(qr, 0.5, return_logits=True)
+    sd = dict(sd)
+    sd["fc3.bias"] = (sd["fc3.bias"] - np.float32(lg.median().item())).astype(np.float32)
+    router = make_router(sd)
+
+    def build(keep):
+        out = {}
+        for i, n in enumerate(names):
+            ix = IndexFlatIP(dims[i])
+            if keep(i):
+                ix.add(corpora[n])
+            out[n] = ix
+        return out
+
+    q_list = [torch.from_numpy(q_by_model[model[n]]).cuda() for n in names]
+    fed = Federation(build(lambda i: True), k, router=router, routing="ragroute", threshold=0.5, dataset="feb4rag")
+    mask = fed.route(qr)
+    D_loc, I_loc = fed.search_sources(q_list, mask)
+    full = fed.merge(D_loc, I_loc, mask)
+    torch.cuda.synchronize()
+    m, Dn, In = mask.cpu().numpy().astype(bool), D_loc.cpu().numpy(), I_loc.cpu().numpy()
+    assert 0.2 < m.mean() < 0.8
+    for b in range(0, B, 9):
+        feats = router_ref.build_features({mm: q_by_model[mm][b] for mm in q_by_model}, names, model, centroids,
+                                          onehot, S, d_max)
+        ref_mask, ref_logits = router_ref.select(sd, feats, 0.5)
+        decided = np.abs(ref_logits) > 1e-5
+        assert np.array_equal(ref_mask[decided], m[b][decided])
+        for s, n in enumerate(names):
+            Ds, Is = Dn[b:b + 1, s * k:(s + 1) * k], In[b:b + 1, s * k:(s + 1) * k]
+            if not m[b, s]:
+                assert (Is == -1).all()
+                continue
+            qv = q_by_model[model[n]][b:b + 1]
+            Dr, Ir = flat_ip.search_seq(qv, corpora[n], k)
+            flat_ip.compare_topk(Ds, Is, Dr, Ir, x=qv, xb=corpora[n])
+    # (b) two ranks, whole-source placement
+    where = place_sources(names, 2)
+    gathered = PackedLists(B, S * k, "cuda", n_blocks=2)
+    for r in range(2):
+        fr = Federation(build(lambda i: where[names[i]] == r), k, router=router, routing="ragroute", threshold=0.5,
+                        dataset="feb4rag")
+        Dr_, Ir_ = fr.search_sources(q_list, mask)
+        gathered.scores(r).copy_(Dr_)
+        gathered.ids(r).copy_(Ir_)
+    s2, i2, _, src2, rank2 = merge_packed(gathered, k, k)
+    torch.cuda.synchronize()
+    assert torch.equal(s2, full["scores"]) and torch.equal(i2, full["ids"]) and torch.equal(src2, full["source"])
+    valid = (src2 >= 0).cpu().numpy()
+    want_rank = np.vectorize(lambda s: where[names[s]] if s >= 0 else -1)(src2.cpu().numpy())
+    assert np.array_equal(rank2.cpu().numpy()[valid], want_rank[valid])
