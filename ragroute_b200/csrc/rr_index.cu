@@ -1135,9 +1135,11 @@ static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Kernel dispatch (measured on B200, full and 1/8-scale MedRAG federation, scripts/gpu_pathcmp*.sh):
 //   nq <= 48            swap-AB scan (rr_scan_tc.cu): lowest fixed cost, HBM-bound
-//   48 < nq <= 256      queries-in-TMEM scan, one CTA per 128-query tile: still HBM-bound, but its
+//   48 < nq <= 128      queries-in-TMEM scan, one CTA per corpus slice: still HBM-bound, but its
 //                       per-thread epilogue keeps up when shards are small (many survivors per tile)
-//   nq > 256            the same on CTA pairs (tensor-bound regime)
+//   nq > 128            decided on the device from the number of ROUTED queries (the host only knows
+//                       the batch size): <= 128 routed -> as above; more -> CTA pairs (256 queries per
+//                       pair; two 128-query single-CTA tiles would pull every corpus tile into two SMs)
 // Dimensions whose query tile does not fit TMEM + shared memory (d_pad > 768) always take the
 // swap-AB scan in passes of <= 64 queries.
 static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
@@ -1145,11 +1147,14 @@ static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
     if (h->scan_path == RR_PATH_GEMM || h->scan_path == RR_PATH_GEMM_PAIR) return true;
     return nq > 48;
 }
+// 1 = one CTA per 128-query tile, 2 = CTA pairs, 0 = both are launched and the device runs the one that fits
+// the number of ROUTED queries (<= 128: single CTAs, more: pairs)
 static int rr_gemm_cta_group(const rr_index* h, int nq) {
     if (h->scan_path == RR_PATH_GEMM) return 1;
     if (h->scan_path == RR_PATH_GEMM_PAIR) return 2;
-    return nq > 2 * RR_GEMM_QTILE ? 2 : 1;
+    return nq > RR_GEMM_QTILE ? 0 : 1;
 }
+static int rr_gemm_qalign(int cta_group) { return RR_GEMM_QTILE * (cta_group == 1 ? 1 : 2); }
 
 // Everything one source needs for one chunk of <= RR_QCHUNK (RR_GEMM_QCHUNK on the large-batch
 // path) queries: which scan it takes and where its scratch lives.
@@ -1186,7 +1191,7 @@ static int rr_plan_chunk(rr_index* h, const float* q_dev, int nq, const uint8_t*
     p->use_gemm = (h->mode == RR_MODE_AUTO) && h->n > 0 && rr_use_gemm_path(h, nq);
     p->use_tc = (h->mode == RR_MODE_AUTO) && p->qt > 0 && h->n > 0 && !p->use_gemm;
     p->gemm_cg = p->use_gemm ? rr_gemm_cta_group(h, nq) : 1;
-    p->nq_pad = (int)rr_align_up((size_t)nq, p->use_gemm ? RR_GEMM_QTILE * p->gemm_cg : RR_TC_MAX_QTILE);
+    p->nq_pad = (int)rr_align_up((size_t)nq, p->use_gemm ? rr_gemm_qalign(p->gemm_cg) : RR_TC_MAX_QTILE);
     p->g_exact = h->sm_count * 2;
     p->cand_stride =
         p->use_gemm ? std::max<int64_t>((int64_t)p->g_exact * RR_EXACT_LIST_DEPTH,
@@ -1196,7 +1201,7 @@ static int rr_plan_chunk(rr_index* h, const float* q_dev, int nq, const uint8_t*
     // second pass (queries whose certificate failed), only when the first pass was a tensor-core scan
     p->use_pass2 = (p->use_tc || p->use_gemm) && rr_gemm_scan_supported(h);
     p->cg2 = rr_gemm_cta_group(h, nq);
-    p->nq_pad2 = p->use_pass2 ? (int)rr_align_up((size_t)nq, (size_t)RR_GEMM_QTILE * p->cg2) : 0;
+    p->nq_pad2 = p->use_pass2 ? (int)rr_align_up((size_t)nq, (size_t)rr_gemm_qalign(p->cg2)) : 0;
     int qsub = RR_EXACT_MAX_QSUB;
     while (qsub > 1 && (size_t)qsub * h->d_pad * sizeof(float) > (96u << 10)) qsub >>= 1;
     p->qsub = qsub;
@@ -1386,8 +1391,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             int rc = rr_gemm_scan_launch(h, p.qbf, nq, p.gemm_cg, p.ctl, p.cand_s, p.cand_r, p.cand_stride, ctr, nullptr,
                                          chain_len > 0 && !no_chain, stream);
             if (rc != RR_OK) return rc;
-            rr_count_launch(1);
-            ++chain_len;
+            rr_count_launch(p.gemm_cg == 0 ? 2 : 1);
+            ++chain_len;  // (the device runs one of the two launches of gemm_cg == 0)
             a.n_lists = 0;
             a.lists_from_ctl = 1;
             a.cpos = p.cpos;
@@ -1476,9 +1481,9 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             ca.cap = RR_COLLECT_CAP;
             int rc = rr_gemm_scan_launch(p.h, p.qbf2, nq, p.cg2, p.ctl2, nullptr, nullptr, 0, nullptr, &ca, n_collect > 0,
                                          stream);
-            ++n_collect;
             if (rc != RR_OK) return rc;
-            rr_count_launch(1);
+            ++n_collect;
+            rr_count_launch(p.cg2 == 0 ? 2 : 1);
         }
         rr_finalize_collect_kernel<<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS,
                                      (size_t)max_dpad * sizeof(float), stream>>>(cf);

@@ -74,6 +74,7 @@ struct GemmParams {
     uint32_t* col_rows;     // [compact query][col_cap]
     int* col_cnt;           // [compact query] (may exceed col_cap: overflow, the caller falls back)
     int col_cap;
+    int min_active, max_active;  // run only if min_active <= routed queries <= max_active (see rr_gemm_scan_launch)
     float* cand_s;  // [compact query][slice][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
@@ -139,7 +140,9 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // 128 * CG (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
     pdl_launch_dependents();  // the next scan of the step may take SMs as they free up
     const int n_active = p.ctl->n_active;
-    if (n_active == 0) {  // no query routed to this source: do not touch the corpus
+    // no query routed to this source: do not touch the corpus; outside [min_active, max_active]: the launch of
+    // the other CTA-group variant right before / after this one takes the chunk
+    if (n_active == 0 || n_active < p.min_active || n_active > p.max_active) {
         pdl_wait_primary();
         return;
     }
@@ -542,12 +545,35 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     return RR_OK;
 }
 
+static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
+                                   float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+                                   const rr_collect_args* collect, int min_active, int max_active, bool chain,
+                                   cudaStream_t stream);
+
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
                         float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
                         const rr_collect_args* collect, bool chain, cudaStream_t stream) {
     RR_REQUIRE(rr_gemm_scan_supported(h), "rr_gemm_scan_launch: d_pad=%d leaves no TMEM for accumulators", h->d_pad);
     RR_REQUIRE(nq >= 1 && nq <= RR_GEMM_QCHUNK, "rr_gemm_scan_launch: nq=%d out of range", nq);
-    RR_REQUIRE(cta_group == 1 || cta_group == 2, "rr_gemm_scan_launch: cta_group must be 1 or 2");
+    RR_REQUIRE(cta_group >= 0 && cta_group <= 2, "rr_gemm_scan_launch: cta_group must be 0 (decide on the device), 1 or 2");
+    if (cta_group == 0) {
+        // Two launches, of which the device runs one: up to 128 ROUTED queries one CTA per corpus slice
+        // (a single query tile: HBM-bound, 148 slices), more than that CTA pairs.  The host only knows the
+        // batch size, not how many of its queries the router sent to this source.
+        int rc = rr_gemm_scan_launch_one(h, qbf16_dev, nq, 1, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
+                                         1, kQTile, chain, stream);
+        if (rc != RR_OK) return rc;
+        return rr_gemm_scan_launch_one(h, qbf16_dev, nq, 2, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
+                                       kQTile + 1, 0x7FFFFFFF, true, stream);
+    }
+    return rr_gemm_scan_launch_one(h, qbf16_dev, nq, cta_group, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
+                                   1, 0x7FFFFFFF, chain, stream);
+}
+
+static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
+                                   float* cand_s, uint32_t* cand_r, int64_t cand_stride, rr_scan_counters* counters_dev,
+                                   const rr_collect_args* collect, int min_active, int max_active, bool chain,
+                                   cudaStream_t stream) {
     // corpus tensor maps: 128-row boxes (shared with the small-batch kernel) or, for CTA pairs, 64-row boxes
     if (h->tmap_hi_ptr != h->hi || h->tmap_hi_rows != h->n) {
         int rc = rr_make_tmap_bf16_rows(&h->tmap_hi, h->hi, h->n, h->d_pad, kNT);
@@ -569,7 +595,8 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
     p.acc_stages = kMaxAcc;
     p.a_tmem_kc = std::min(p.num_kc, kMaxATmemKc);
     p.a_smem_kc = p.num_kc - p.a_tmem_kc;
-    if (nq <= kQTile && cta_group == 1 && h->gemm_tmem_all && p.num_kc * 32 + kNT <= (int)kTmemCols) {
+    if ((nq <= kQTile || max_active <= kQTile) && cta_group == 1 && h->gemm_tmem_all &&
+        p.num_kc * 32 + kNT <= (int)kTmemCols) {
         // one query tile = the HBM-bound regime (intensity <= 128 flop/byte): the tensor pipe has slack, so the
         // whole tile goes to TMEM with ONE accumulator stage (the MMAs of the next corpus tile wait for the
         // epilogue's tcgen05.ld, a fraction of the tile's HBM time) and the shared memory it frees becomes
@@ -588,12 +615,15 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
     p.cand_s = cand_s;
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
+    p.min_active = min_active;
+    p.max_active = max_active;
     p.theta = collect ? collect->theta : nullptr;
     p.col_rows = collect ? collect->rows : nullptr;
     p.col_cnt = collect ? collect->cnt : nullptr;
     p.col_cap = collect ? collect->cap : 0;
     RR_REQUIRE(collect || (int64_t)h->sm_count * kDepth <= cand_stride, "rr_gemm_scan_launch: candidate stride too small");
     // the tail of each query tile is fetched by TMA from the bf16 query buffer
+    // (the caller pads the buffer to 256 rows whenever the pair variant may run)
     const int q_align = kQTile * cta_group;
     const int nq_rows = (nq + q_align - 1) / q_align * q_align;
     alignas(64) CUtensorMap tq;
