@@ -66,23 +66,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(cons
     lane_best(keys, L, lane, bk, bp);
     int n_out = k;
     for (int r = 0; r < k; ++r) {
-        // warp arg-max over (key desc, position asc)
-        uint32_t wk = bk;
-        int wp = bp;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const uint32_t ok = __shfl_xor_sync(RR_FULL, wk, o);
-            const int op = __shfl_xor_sync(RR_FULL, wp, o);
-            const bool take = (op >= 0) && (wp < 0 || ok > wk || (ok == wk && op < wp));
-            if (take) {
-                wk = ok;
-                wp = op;
-            }
-        }
-        if (wp < 0) {  // fewer than k live entries
+        // warp arg-max over (key desc, position asc): two warp reductions (redux.sync) -- the largest key,
+        // then the lowest position among the lanes holding it.  Key 0 never occurs (it is a NaN pattern,
+        // and NaNs are dead), so it stands for "lane has nothing left".
+        const uint32_t wk = __reduce_max_sync(RR_FULL, bp >= 0 ? bk : 0u);
+        const uint32_t wpu = __reduce_min_sync(RR_FULL, (bp >= 0 && bk == wk) ? (uint32_t)bp : 0xFFFFFFFFu);
+        if (wpu == 0xFFFFFFFFu) {  // fewer than k live entries
             n_out = r;
             break;
         }
+        const int wp = (int)wpu;
         if (lane == 0) wins[r] = wp;
         if ((wp & 31) == lane) {  // owner of the winning slot retires it and rescans
             keys[wp] = kDead;

@@ -431,6 +431,50 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     for (int j = 0; j < 32; ++j)
                         if (c * 32 + j >= valid) r[c][j] = __float_as_uint(RR_NEG_INF);
             }
+            if (!COLLECT && tile == slice && qg < n_active) {
+                // First tile of the launch: the list is empty, so all 128 scores would "survive" and go
+                // through 128 one-by-one inserts while the tensor pipe and the TMA ring wait.  Seed the
+                // list with the two best of each group of 8 columns instead (32 entries, branch-free) and
+                // send only what beats their minimum through the regular path.
+                static_assert(kDepth == 32 && kNT == 128, "seeding fills 2 x 16 groups");
+                float mn = __builtin_huge_valf();
+                int mn_e = 0;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    float a1 = RR_NEG_INF, a2 = RR_NEG_INF;
+                    int j1 = 0, j2 = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float v = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
+                        if (v > a1) {
+                            a2 = a1;
+                            j2 = j1;
+                            a1 = v;
+                            j1 = j;
+                        } else if (v > a2) {
+                            a2 = v;
+                            j2 = j;
+                        }
+                    }
+                    ls[(2 * g) * kQTile + t] = a1;
+                    lr[(2 * g) * kQTile + t] = (a1 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j1) : RR_NO_ROW;
+                    ls[(2 * g + 1) * kQTile + t] = a2;
+                    lr[(2 * g + 1) * kQTile + t] = (a2 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j2) : RR_NO_ROW;
+                    if (a1 < mn) {
+                        mn = a1;
+                        mn_e = 2 * g;
+                    }
+                    if (a2 < mn) {
+                        mn = a2;
+                        mn_e = 2 * g + 1;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j == j1 || j == j2) r[g >> 2][(g & 3) * 8 + j] = __float_as_uint(RR_NEG_INF);
+                }
+                thr = mn;  // -inf (and pos = an empty slot) when the tile had fewer than 32 rows
+                pos = mn_e;
+            }
             // maxima of the 16 groups of 8 columns, then of the tile: hits are sparse (a few
             // per warp and tile), so whole groups are skipped with one vote each
             float m8[16];

@@ -1,8 +1,10 @@
 #!/bin/bash
 # ncu evidence for the dominant kernels (one GPU).  Usage: bash scripts/gpu_profile.sh <tag>
 # 1) launch list (gpu__time_duration per launch of every rr_* kernel) of the default bench command, short
-# 2) --set full capture of the large-batch scan kernel (CTA pairs) on a PubMed-shaped slice (6M x 768, >> L2), batch 1024
-# 3) --set full capture of the small-batch scan kernel on the same slice, batch 64
+# 2) launch list of the 1/8-scale federation (the per-GPU shard of an 8-GPU run) at batch 64 and 1
+# 3) --set full capture of the large-batch scan kernel (CTA pairs) on a PubMed-shaped slice (6M x 768, >> L2), batch 2048
+# 4) --set full capture of the small-batch scan kernel on the same slice, batch 32
+# Every ncu command runs only after the same command exited 0 without ncu.
 TAG=${1:-r01}
 mkdir -p gpurun_out
 CMD1="python bench.py --steps 4 --warmup 3 --no-cpu-baseline --sweep 8,64"
@@ -10,9 +12,14 @@ $CMD1 > gpurun_out/${TAG}_plain1.json 2> gpurun_out/${TAG}_plain1.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 600 --csv \
     --log-file gpurun_out/${TAG}_launches.csv $CMD1 > gpurun_out/${TAG}_ncu1.out 2>&1
 echo "launch list exit=$?"
+CMD1B="python bench.py --rows-scale 0.125 --batch 64 --steps 4 --warmup 3 --no-cpu-baseline --sweep 1"
+$CMD1B > gpurun_out/${TAG}_plain1b.json 2> gpurun_out/${TAG}_plain1b.err &&
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 400 --csv \
+    --log-file gpurun_out/${TAG}_launches_small.csv $CMD1B > gpurun_out/${TAG}_ncu1b.out 2>&1
+echo "small launch list exit=$?"
 CMD2="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 2048 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD2 > gpurun_out/${TAG}_plain2.json 2> gpurun_out/${TAG}_plain2.err &&
-ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<2, (false|0)>' -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
 echo "gemm capture exit=$?"
 CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 32 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
@@ -20,3 +27,8 @@ $CMD3 > gpurun_out/${TAG}_plain3.json 2> gpurun_out/${TAG}_plain3.err &&
 ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_scan $CMD3 > gpurun_out/${TAG}_ncu3.out 2>&1
 echo "scan capture exit=$?"
+CMD4="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
+$CMD4 > gpurun_out/${TAG}_plain4.json 2> gpurun_out/${TAG}_plain4.err &&
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<1, (false|0)>' -s 3 -c 1 \
+    -f -o gpurun_out/${TAG}_gemm64 $CMD4 > gpurun_out/${TAG}_ncu4.out 2>&1
+echo "gemm64 capture exit=$?"
