@@ -1134,8 +1134,8 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
 static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // Kernel dispatch (measured on B200, full and 1/8-scale MedRAG federation, scripts/gpu_pathcmp*.sh):
-//   nq <= 48            swap-AB scan (rr_scan_tc.cu): lowest fixed cost, HBM-bound
-//   48 < nq <= 128      queries-in-TMEM scan, one CTA per corpus slice: still HBM-bound, but its
+//   nq <= 24            swap-AB scan (rr_scan_tc.cu): lowest fixed cost, HBM-bound (7.1-7.3 TB/s)
+//   24 < nq <= 128      queries-in-TMEM scan, one CTA per corpus slice: still HBM-bound, but its
 //                       per-thread epilogue keeps up when shards are small (many survivors per tile)
 //   nq > 128            decided on the device from the number of ROUTED queries (the host only knows
 //                       the batch size): <= 128 routed -> as above; more -> CTA pairs (256 queries per
@@ -1148,7 +1148,7 @@ static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
     // (also for small shards: at 64 queries per pass the swap-AB scan's cooperative list warm-up costs more
     // than this kernel's fixed ~40 us -- measured 80 vs 57 us on a 37 k-row shard -- and mixing the two
     // paths in one step would split its batched launches)
-    return nq > 48;
+    return nq > 24;
 }
 // 1 = one CTA per 128-query tile, 2 = CTA pairs, 0 = both are launched and the device runs the one that fits
 // the number of ROUTED queries (<= 128: single CTAs, more: pairs)
@@ -1517,9 +1517,12 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             a.qsub = p.qsub;
             min_qsub = std::min(min_qsub, p.qsub);
         }
-        // one launch covers every sub-batch of every source; blocks beyond the failing queries exit at once
+        // one launch covers every sub-batch of every source (the kernel strides over them); blocks exit at
+        // once when nothing is left for the exact scan -- the normal case after a tensor-core pass, so only
+        // exact-only plans get extra rows of blocks
         const int g_exact = plans[0].g_exact;
-        const dim3 grid((unsigned)g_exact, (unsigned)std::min(4, (nq + min_qsub - 1) / min_qsub), (unsigned)S);
+        const int gy = any_first ? 1 : std::min(4, (nq + min_qsub - 1) / min_qsub);
+        const dim3 grid((unsigned)g_exact, (unsigned)gy, (unsigned)S);
         rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, max_ex_smem, stream>>>(ea);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);

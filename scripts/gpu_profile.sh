@@ -19,7 +19,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:rr_ -c 400 --
 echo "small launch list exit=$?"
 CMD2="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 2048 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD2 > gpurun_out/${TAG}_plain2.json 2> gpurun_out/${TAG}_plain2.err &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<2, (false|0)>' -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<\(int\)2, \(bool\)0>' -s 3 -c 1 \
+    -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
+# (fallback: per step the matching launches are <1,0> no-op, <2,0>, <1,1> no-op, <2,1> no-op)
+[ -f gpurun_out/${TAG}_gemm.ncu-rep ] || ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 13 -c 1 \
     -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
 echo "gemm capture exit=$?"
 CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 32 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
@@ -29,6 +32,8 @@ ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 
 echo "scan capture exit=$?"
 CMD4="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 64 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD4 > gpurun_out/${TAG}_plain4.json 2> gpurun_out/${TAG}_plain4.err &&
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<1, (false|0)>' -s 3 -c 1 \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<\(int\)1, \(bool\)0>' -s 3 -c 1 \
+    -f -o gpurun_out/${TAG}_gemm64 $CMD4 > gpurun_out/${TAG}_ncu4.out 2>&1
+[ -f gpurun_out/${TAG}_gemm64.ncu-rep ] || ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 6 -c 1 \
     -f -o gpurun_out/${TAG}_gemm64 $CMD4 > gpurun_out/${TAG}_ncu4.out 2>&1
 echo "gemm64 capture exit=$?"
