@@ -401,23 +401,26 @@ struct rr_finalize_args {
     const int* cpos;   // large-batch path: candidate row of query qi (compacted); NULL = qi
     int lists_from_ctl;  // large-batch path: the number of lists is ctl->n_lists (decided on the device)
     int enabled;       // 0: this source takes no part in the launch
+    int nq;            // queries of the chunk
+    int stage_cap;     // candidate entries the block's dynamic shared memory can stage (more: read in place)
+    const int* work_list;   // RESCORE = false after a tensor-core pass: only these queries need the block ...
+    const int* work_count;  // ... (a few blocks stride over them; normally the list is empty)
 };
 
 constexpr int RR_FIN_THREADS = 512;
 constexpr int RR_FIN_MAXSEL = 256;
 
 // dynamic shared memory of a finalize block: the query (RESCORE) + the staged candidate lists
-static size_t rr_finalize_smem(bool rescore, int d_pad, int64_t cand_stride) {
-    return (rescore ? (size_t)d_pad * sizeof(float) : 0) + (size_t)cand_stride * 8;
+static size_t rr_finalize_smem(bool rescore, int d_pad, int64_t stage_cap) {
+    return (rescore ? (size_t)d_pad * sizeof(float) : 0) + (size_t)stage_cap * 8;
 }
 
-template <bool RESCORE>
-__global__ void __launch_bounds__(RR_FIN_THREADS)
-rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
-    const rr_finalize_args& a = m.s[blockIdx.y];
-    if (!a.enabled) return;
-    const int qi = blockIdx.x;
+// one query of one source; called by every thread of the block (blockDim.x = 256 or 512)
+// CH = chunks of 256 dimensions each warp keeps in flight per row while rescoring (registers vs. latency)
+template <bool RESCORE, int CH>
+__device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const int qi) {
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int n_threads = blockDim.x;
     float* Dq = a.D + (int64_t)qi * a.out_stride;
     int64_t* Iq = a.I + (int64_t)qi * a.out_stride;
     if (RESCORE) {
@@ -448,14 +451,20 @@ rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
     __shared__ uint32_t sel_r[RR_FIN_MAXSEL];
     extern __shared__ __align__(16) unsigned char fin_sm[];
     float* q_sm = reinterpret_cast<float*>(fin_sm);                               // [d_pad] (RESCORE only)
-    float* cs = reinterpret_cast<float*>(fin_sm) + (RESCORE ? a.d_pad : 0);       // [n_cand] staged scores
-    uint32_t* cr = reinterpret_cast<uint32_t*>(cs + a.cand_stride);               // [n_cand] staged rows
+    float* cs_sm = reinterpret_cast<float*>(fin_sm) + (RESCORE ? a.d_pad : 0);    // [stage_cap] staged scores
+    uint32_t* cr_sm = reinterpret_cast<uint32_t*>(cs_sm + a.stage_cap);           // [stage_cap] staged rows
 
     const int crow = (RESCORE && a.cpos) ? a.cpos[qi] : qi;
     const float* gs = a.cand_s + (int64_t)crow * a.cand_stride;
     const uint32_t* gr = a.cand_r + (int64_t)crow * a.cand_stride;
     const int n_lists = (RESCORE && a.lists_from_ctl) ? a.ctl->n_lists : a.n_lists;
     const int n_cand = n_lists * a.depth;
+    // the select below makes 5-9 passes over the lists: from shared memory when they fit the block's
+    // allotment (sized by the host for the batch: everything for small batches, 2048 entries -- and more
+    // blocks per SM -- for large ones, whose lists are few), else in place
+    const bool staged = n_cand <= a.stage_cap;
+    const float* cs = staged ? cs_sm : gs;
+    const uint32_t* cr = staged ? cr_sm : gr;
 
     if (tid == 0) {
         s_prefix = 0ull;
@@ -468,28 +477,30 @@ rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
         const float* qr = a.q + (int64_t)qi * a.d;
         for (int e = tid; e < a.d_pad; e += blockDim.x) q_sm[e] = (e < a.d) ? qr[e] : 0.f;
     }
-    // stage the lists once (the select below makes 5-9 passes over them); count the occupied slots and take
-    // T = largest tail of a full list (every row a list dropped scores <= its tail)
+    // stage the lists; count the occupied slots and take T = largest tail of a full list (every row a
+    // list dropped scores <= its tail)
     float T = RR_NEG_INF;
     int nv = 0;
     {
         constexpr int U = 4;
         const int depth_m1 = a.depth - 1;
-        for (int i0 = tid; i0 < n_cand; i0 += RR_FIN_THREADS * U) {
+        for (int i0 = tid; i0 < n_cand; i0 += n_threads * U) {
             float vs[U];
             uint32_t vr[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * RR_FIN_THREADS;
+                const int i = i0 + u * n_threads;
                 vs[u] = (i < n_cand) ? __ldg(gs + i) : RR_NEG_INF;
                 vr[u] = (i < n_cand) ? __ldg(gr + i) : RR_NO_ROW;
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int i = i0 + u * RR_FIN_THREADS;
+                const int i = i0 + u * n_threads;
                 if (i < n_cand) {
-                    cs[i] = vs[u];
-                    cr[i] = vr[u];
+                    if (staged) {
+                        cs_sm[i] = vs[u];
+                        cr_sm[i] = vr[u];
+                    }
                     if (vr[u] != RR_NO_ROW) {
                         ++nv;
                         if ((i & depth_m1) == depth_m1) T = fmaxf(T, vs[u]);  // list depths are powers of two
@@ -507,7 +518,7 @@ rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
     }
     __syncthreads();
     T = s_red[0];
-    for (int i = 1; i < RR_FIN_THREADS / 32; ++i) T = fmaxf(T, s_red[i]);
+    for (int i = 1; i < (n_threads >> 5); ++i) T = fmaxf(T, s_red[i]);
     const int n_valid = s_nvalid;
     const int want = RESCORE ? min(a.kprime, RR_FIN_MAXSEL) : a.k;
     const int kp = min(want, n_valid);
@@ -605,8 +616,8 @@ rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
         // exact rescoring: fp32 row rebuilt from the planes, fp64 accumulation.  One warp per row, RB rows x
         // CH chunks of 256 dimensions per warp in flight at once (the gathers are random 16-byte reads of
         // both planes: latency-bound, so 16 warps x 12 loads cover 128 rows x 768 dims in 4 round trips)
-        constexpr int RB = 2, CH = 3;
-        constexpr int NW = RR_FIN_THREADS / 32;
+        constexpr int RB = 2;
+        const int NW = n_threads >> 5;
         for (int i0 = w * RB; i0 < kp; i0 += NW * RB) {
             double acc[RB];
             int64_t rowo[RB];
@@ -720,6 +731,29 @@ rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
     }
 }
 
+// grid = (queries, sources), or (a few blocks, sources) striding over a work list.
+// BIG = false: small batches, latency-bound: 512 threads, 6 gathers in flight per lane while rescoring.
+// BIG = true: large batches, throughput-bound: 256 threads and <= 64 registers, 4 blocks per SM.
+template <bool RESCORE, bool BIG>
+__global__ void __launch_bounds__(BIG ? RR_FIN_THREADS / 2 : RR_FIN_THREADS, BIG ? 4 : 1)
+rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
+    const rr_finalize_args& a = m.s[blockIdx.y];
+    if (!a.enabled) return;
+    constexpr int CH = BIG ? 1 : 3;
+    if (!RESCORE && a.work_list) {
+        const int n = *a.work_count;
+        for (int wi = blockIdx.x; wi < n; wi += gridDim.x) {
+            rr_finalize_one<RESCORE, CH>(a, a.work_list[wi]);
+            __syncthreads();  // the block's shared state is reused by the next query
+        }
+        return;
+    }
+    for (int qi = blockIdx.x; qi < a.nq; qi += gridDim.x) {
+        rr_finalize_one<RESCORE, CH>(a, qi);
+        __syncthreads();
+    }
+}
+
 // ---- second pass ("collect") for the queries whose certificate failed --------------------------
 // Gather their bf16 rows (in fail_list order) into the second query buffer, hand their thresholds to
 // the scan, zero their row counters.  grid = rows of the second buffer, 128 threads.
@@ -741,26 +775,29 @@ struct rr_prep_collect_args {
 __global__ void __launch_bounds__(128)
 rr_prep_collect_kernel(const __grid_constant__ rr_multi<rr_prep_collect_args> m) {
     const rr_prep_collect_args& a = m.s[blockIdx.y];
-    const int i = blockIdx.x;
-    if (i >= a.nq_pad2) return;
+    if (a.nq_pad2 == 0) return;
     const int d_pad = a.d_pad;
     const int n_fail = a.ctl->n_fail;
-    if (i == 0 && threadIdx.x == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         a.ctl2->n_active = n_fail;
         a.ctl2->any_active = n_fail > 0;
     }
     if (n_fail == 0) return;  // nothing failed: the scan that follows exits at once, leave the buffer alone
-    uint4* out = reinterpret_cast<uint4*>(a.qbf2 + (int64_t)i * d_pad);
-    if (i < n_fail) {
-        const int qi = a.fail_list[i];
-        const uint4* in = reinterpret_cast<const uint4*>(a.qbf16 + (int64_t)(a.cpos ? a.cpos[qi] : qi) * d_pad);
-        for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = in[e];
-        if (threadIdx.x == 0) a.theta2[i] = a.theta_q[qi];
-    } else {
-        for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = make_uint4(0, 0, 0, 0);
-        if (threadIdx.x == 0) a.theta2[i] = __builtin_huge_valf();
+    // the rows of the second buffer its scan can touch: the failing queries, zero padded to whole query tiles
+    const int n_rows = min(a.nq_pad2, (n_fail + 255) / 256 * 256);
+    for (int i = blockIdx.x; i < n_rows; i += gridDim.x) {
+        uint4* out = reinterpret_cast<uint4*>(a.qbf2 + (int64_t)i * d_pad);
+        if (i < n_fail) {
+            const int qi = a.fail_list[i];
+            const uint4* in = reinterpret_cast<const uint4*>(a.qbf16 + (int64_t)(a.cpos ? a.cpos[qi] : qi) * d_pad);
+            for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = in[e];
+            if (threadIdx.x == 0) a.theta2[i] = a.theta_q[qi];
+        } else {
+            for (int e = threadIdx.x; e < d_pad / 8; e += blockDim.x) out[e] = make_uint4(0, 0, 0, 0);
+            if (threadIdx.x == 0) a.theta2[i] = __builtin_huge_valf();
+        }
+        if (threadIdx.x == 0 && i < a.nq) a.col_cnt[i] = 0;
     }
-    if (threadIdx.x == 0 && i < a.nq) a.col_cnt[i] = 0;
 }
 
 constexpr int RR_COLLECT_CAP = 2048;  // rows a failing query may collect before it goes to the exact scan
@@ -789,11 +826,7 @@ struct rr_collect_fin_args {
 // One block per failing query: every row that can possibly belong to its top-k was collected; score
 // them exactly (fp32 rows rebuilt from the planes, fp64 accumulate) and keep the k best by
 // (score desc, row asc) -- no certificate needed.  A query whose list overflowed goes to the exact scan.
-__global__ void __launch_bounds__(RR_FIN_THREADS)
-rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args> m) {
-    const rr_collect_fin_args& a = m.s[blockIdx.y];
-    const int i = blockIdx.x;
-    if (!a.enabled || i >= a.ctl->n_fail) return;
+__device__ __forceinline__ void rr_finalize_collect_one(const rr_collect_fin_args& a, const int i) {
     const int qi = a.fail_list[i];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     const int cnt = a.col_cnt[i];
@@ -817,7 +850,7 @@ rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args>
     }
     __syncthreads();
     constexpr int RB = 4;
-    constexpr int NW = RR_FIN_THREADS / 32;
+    const int NW = blockDim.x >> 5;
     for (int i0 = w * RB; i0 < cnt; i0 += NW * RB) {
         double acc[RB];
 #pragma unroll
@@ -886,6 +919,18 @@ rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args>
         Iq[x] = ok ? (int64_t)s_r[x] + a.id_offset : (int64_t)-1;
     }
     if (tid == 0) a.fail_flags[qi] = 0;  // settled: the exact finalize skips it
+}
+
+// grid = (a few blocks, sources): the blocks stride over the failing queries (normally none)
+__global__ void __launch_bounds__(RR_FIN_THREADS)
+rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args> m) {
+    const rr_collect_fin_args& a = m.s[blockIdx.y];
+    if (!a.enabled) return;
+    const int n_fail = a.ctl->n_fail;
+    for (int i = blockIdx.x; i < n_fail; i += gridDim.x) {
+        rr_finalize_collect_one(a, i);
+        __syncthreads();  // the block's shared lists are reused by the next query
+    }
 }
 
 // ------------------------------------------------------------------- host ---
@@ -1295,10 +1340,19 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         any_rows |= p.h->n > 0;
     }
 
-    size_t fin_smem[2] = {0, 0};  // [RESCORE]
+    // finalize blocks: small batches are latency-bound (one block per (query, source) of 512 threads, all
+    // candidate lists staged in shared memory); large batches are throughput-bound and their lists are few
+    // (one per corpus slice): 256 threads and 16 KB of staging, so that 8 blocks share an SM
+    const bool fin_small = (int64_t)nq * S <= 4 * (int64_t)plans[0].h->sm_count;
+    const int fin_threads = fin_small ? RR_FIN_THREADS : RR_FIN_THREADS / 2;
+    int64_t stage_cap = 2048;
+    if (fin_small)
+        for (int s = 0; s < S; ++s) stage_cap = std::max(stage_cap, plans[s].cand_stride);
+    const int fin_blocks_sparse = std::min(nq, 64);  // launches that normally find nothing to do
+    size_t fin_smem[2] = {0, 0};                     // [RESCORE]
     for (int s = 0; s < S; ++s)
         for (int r = 0; r < 2; ++r)
-            fin_smem[r] = std::max(fin_smem[r], rr_finalize_smem(r != 0, plans[s].h->d_pad, plans[s].cand_stride));
+            fin_smem[r] = std::max(fin_smem[r], rr_finalize_smem(r != 0, plans[s].h->d_pad, stage_cap));
     RR_REQUIRE(fin_smem[1] <= (200u << 10), "dimension %d too large for the finalize kernel", max_dpad);
     int dev = 0;
     RR_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1306,8 +1360,10 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
     if (!attr_done[dev & 63]) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_exact_scan_kernel<RR_EXACT_MAX_QSUB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         attr_done[dev & 63] = true;
     }
 
@@ -1369,6 +1425,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         a.pad_inactive = (p.use_tc || p.use_gemm) ? 0 : 1;
         a.theta_q = p.use_pass2 ? p.theta_q : nullptr;
         a.enabled = (p.use_tc || p.use_gemm) ? 1 : 0;
+        a.nq = nq;
+        a.stage_cap = (int)stage_cap;
     }
 
     // ---- first pass: bf16 tensor-core scan of every source, then one finalize for all of them.  The scans
@@ -1420,7 +1478,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         if (rc != RR_OK) return rc;
     }
     if (any_first) {
-        rr_finalize_kernel<true><<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS, fin_smem[1], stream>>>(fa);
+        if (fin_small) rr_finalize_kernel<true, false><<<dim3((unsigned)nq, (unsigned)S), fin_threads, fin_smem[1], stream>>>(fa);
+        else rr_finalize_kernel<true, true><<<dim3((unsigned)nq, (unsigned)S), fin_threads, fin_smem[1], stream>>>(fa);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
     }
@@ -1470,7 +1529,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             c.out_stride = p.out_stride;
             c.enabled = 1;
         }
-        rr_prep_collect_kernel<<<dim3((unsigned)max_nq_pad2, (unsigned)S), 128, 0, stream>>>(pc);
+        rr_prep_collect_kernel<<<dim3((unsigned)std::min(max_nq_pad2, 256), (unsigned)S), 128, 0, stream>>>(pc);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
         int n_collect = 0;
@@ -1488,7 +1547,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             ++n_collect;
             rr_count_launch(p.cg2 == 0 ? 2 : 1);
         }
-        rr_finalize_collect_kernel<<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS,
+        rr_finalize_collect_kernel<<<dim3((unsigned)fin_blocks_sparse, (unsigned)S), RR_FIN_THREADS,
                                      (size_t)max_dpad * sizeof(float), stream>>>(cf);
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
@@ -1527,15 +1586,29 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
     }
+    // after a tensor-core pass only the queries the second pass could not settle are left (normally none):
+    // a few blocks stride over that list; an exact-only plan visits every query (and pads the unrouted ones)
+    bool all_sparse = true;
     for (int s = 0; s < S; ++s) {
+        const rr_chunk_plan& p = plans[s];
         rr_finalize_args& a = fa.s[s];
-        a.n_lists = (plans[s].h->n > 0) ? plans[s].g_exact : 0;
+        a.n_lists = (p.h->n > 0) ? p.g_exact : 0;
         a.depth = RR_EXACT_LIST_DEPTH;
         a.lists_from_ctl = 0;
         a.cpos = nullptr;
         a.enabled = 1;
+        if (p.use_tc || p.use_gemm) {
+            a.work_list = p.use_pass2 ? p.fail2_list : p.fail_list;
+            a.work_count = p.use_pass2 ? &p.ctl->n_fail2 : &p.ctl->n_fail;
+        } else {
+            a.work_list = nullptr;
+            a.work_count = nullptr;
+            all_sparse = false;
+        }
     }
-    rr_finalize_kernel<false><<<dim3((unsigned)nq, (unsigned)S), RR_FIN_THREADS, fin_smem[0], stream>>>(fa);
+    const dim3 fgrid((unsigned)(all_sparse ? fin_blocks_sparse : nq), (unsigned)S);
+    if (fin_small) rr_finalize_kernel<false, false><<<fgrid, fin_threads, fin_smem[0], stream>>>(fa);
+    else rr_finalize_kernel<false, true><<<fgrid, fin_threads, fin_smem[0], stream>>>(fa);
     RR_CUDA_CHECK(cudaGetLastError());
     rr_count_launch(1);
     return RR_OK;
