@@ -373,8 +373,9 @@ def gpu_main(args, rows, workload):
         if not n:
             return {"bound": None, "achieved": None, "peak": None, "frac": None, "traffic": None}
         small = batch <= 256  # one 128-query tile per CTA or the swap-AB scan: HBM-bound
-        key = "rr_tc_scan_kernel" if (batch <= 48 and args.scan_path == 0) or args.scan_path == 1 else "rr_gemm_scan_kernel"
-        tj = traffic_db.get(key, {})
+        # dispatch of rr_index.cu: swap-AB scan up to 24 queries, queries-in-TMEM scan above
+        key = "rr_tc_scan_kernel" if (batch <= 24 and args.scan_path == 0) or args.scan_path == 1 else "rr_gemm_scan_kernel"
+        tj = traffic_db.get(key + "_small_batch" if (key == "rr_gemm_scan_kernel" and small) else key) or traffic_db.get(key, {})
         traffic = tj.get("dram_over_algorithmic", 0) * run["scan_bytes"] / n if tj else None
         common = {"kernel": key, "launches_timed": n, "avg_launch_ms": run["scan_ms"] / n,
                   "kernel_share_of_step": run["scan_ms"] / max(run["ms_total"], 1e-9),

@@ -3,7 +3,8 @@
 # 1) launch list (gpu__time_duration per launch of every rr_* kernel) of the default bench command, short
 # 2) launch list of the 1/8-scale federation (the per-GPU shard of an 8-GPU run) at batch 64 and 1
 # 3) --set full capture of the large-batch scan kernel (CTA pairs) on a PubMed-shaped slice (6M x 768, >> L2), batch 2048
-# 4) --set full capture of the small-batch scan kernel on the same slice, batch 32
+# 4) --set full capture of the small-batch (swap-AB) scan kernel on the same slice, batch 16
+# 5) --set full capture of the queries-in-TMEM scan in its HBM-bound regime (one CTA per slice), batch 64
 # Every ncu command runs only after the same command exited 0 without ncu.
 TAG=${1:-r01}
 mkdir -p gpurun_out
@@ -25,7 +26,7 @@ ncu --set full --clock-control none --import-source on --kernel-name-base demang
 [ -f gpurun_out/${TAG}_gemm.ncu-rep ] || ncu --set full --clock-control none --import-source on -k regex:rr_gemm_scan -s 13 -c 1 \
     -f -o gpurun_out/${TAG}_gemm $CMD2 > gpurun_out/${TAG}_ncu2.out 2>&1
 echo "gemm capture exit=$?"
-CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 32 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
+CMD3="python bench.py --workload pubmed --rows-scale 0.25 --routing all --batch 16 --steps 3 --warmup 3 --no-cpu-baseline --sweep="
 $CMD3 > gpurun_out/${TAG}_plain3.json 2> gpurun_out/${TAG}_plain3.err &&
 ncu --set full --clock-control none --import-source on -k regex:rr_tc_scan -s 3 -c 1 \
     -f -o gpurun_out/${TAG}_scan $CMD3 > gpurun_out/${TAG}_ncu3.out 2>&1
