@@ -451,7 +451,7 @@ def gpu_main(args, rows, workload):
                              if need / 2 > (512 << 20) else "corpus comparable to L2: re-scans may hit L2"},
             "p50_ms": pct(dev_run["per_step"], 50), "p99_ms": pct(dev_run["per_step"], 99),
             "e2e": {"value": qps_e2e, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
-                    "d2h_bytes_per_step": B * K * (4 + 8 + 8), "ms_per_step": e2e_run["ms_total"] / args.steps,
+                    "d2h_bytes_per_step": B * K * (4 + 8 + 4), "ms_per_step": e2e_run["ms_total"] / args.steps,
                     "p50_ms": pct(e2e_run["per_step"], 50), "p99_ms": pct(e2e_run["per_step"], 99)},
             "gpu_launches": dev_run["launches"],
             "roofline": roofline_of(dev_run, B),

@@ -99,20 +99,36 @@ class PackedLists:
         return out
 
 
-def merge_packed(lists: PackedLists, k: int, list_len: int, descending: bool = True):
+class MergeOut:
+    """Result of one merge as ONE device byte block: [ids int64 | scores fp32 | source int32 | rank int32 |
+    pos int32], each [B, k] -- so a host caller fetches (ids, scores, source) with a single copy."""
+
+    def __init__(self, B: int, k: int, device):
+        self.B, self.k = B, k
+        n = B * k
+        self.buf = torch.empty(n * 24, dtype=torch.uint8, device=device)
+        self.ids = self.buf[:8 * n].view(torch.int64).view(B, k)
+        self.scores = self.buf[8 * n:12 * n].view(torch.float32).view(B, k)
+        self.source = self.buf[12 * n:16 * n].view(torch.int32).view(B, k)
+        self.rank = self.buf[16 * n:20 * n].view(torch.int32).view(B, k)
+        self.pos = self.buf[20 * n:24 * n].view(torch.int32).view(B, k)
+        self.host_bytes = 16 * n  # ids, scores, source
+
+
+def merge_packed(lists: PackedLists, k: int, list_len: int, descending: bool = True,
+                 out: Optional[MergeOut] = None):
     """Merge every block of `lists` ([B, n_blocks * L] in block-major order) on the GPU.
     Returns (scores [B,k], ids [B,k], pos, source, rank int32 [B,k])."""
     B, dev = lists.B, lists.buf.device
     with torch.cuda.device(dev):
-        os_ = torch.empty((B, k), dtype=torch.float32, device=dev)
-        oi = torch.empty((B, k), dtype=torch.int64, device=dev)
-        meta = torch.empty((3, B, k), dtype=torch.int32, device=dev)
+        o = out if out is not None else MergeOut(B, k, dev)
+        assert o.B == B and o.k == k
         base = lists.buf.data_ptr()
         _lib.check(_lib.load().rr_merge_topk_segments(
             base, base + lists.n_scores, B, lists.n_blocks, lists.L, lists.block_bytes // 4, lists.block_bytes // 8,
-            int(k), 1 if descending else 0, int(list_len), os_.data_ptr(), oi.data_ptr(), meta[0].data_ptr(),
-            meta[1].data_ptr(), meta[2].data_ptr(), torch.cuda.current_stream().cuda_stream))
-    return os_, oi, meta[0], meta[1], meta[2]
+            int(k), 1 if descending else 0, int(list_len), o.scores.data_ptr(), o.ids.data_ptr(), o.pos.data_ptr(),
+            o.source.data_ptr(), o.rank.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return o.scores, o.ids, o.pos, o.source, o.rank
 
 
 class Federation:
@@ -139,6 +155,7 @@ class Federation:
         self.distributed = distributed
         self.fused = fused  # False: one rr_index_search_ex call per source (testing)
         self._packed: Optional[PackedLists] = None
+        self._host_out: Dict[int, torch.Tensor] = {}  # pinned result buffers of search_host, per batch size
         self._rng = random.Random(seed)
         if router is not None and routing == "ragroute":
             assert list(router.data_sources) == self.names, "router and federation must list sources in the same order"
@@ -206,19 +223,27 @@ class Federation:
             packed.ids().copy_(I_loc)
         if self.distributed:
             packed = packed.gather(self.group)
-        scores, ids, _, src, rank = merge_packed(packed, k, k, descending=self.descending)
-        return {"scores": scores, "ids": ids, "source": src, "rank": rank, "mask": mask}
+        out = MergeOut(packed.B, k, packed.buf.device)
+        scores, ids, _, src, rank = merge_packed(packed, k, k, descending=self.descending, out=out)
+        return {"scores": scores, "ids": ids, "source": src, "rank": rank, "mask": mask, "_block": out}
 
     # -- host-buffer entry point (what a server process calls) --------------------------
     def search_host(self, q_host: torch.Tensor):
-        """q_host: pinned CPU tensor [B, d].  Copies in, runs the step, copies the
-        top-k (scores, ids, source) out and synchronises."""
+        """q_host: pinned CPU tensor [B, d].  Copies in, runs the step, copies the top-k
+        (scores, ids, source) out -- one device-to-host copy of 16 k bytes per query into a pinned
+        buffer kept per batch size -- and synchronises.  The returned arrays are views of that buffer:
+        valid until the next call with the same batch size."""
         q = q_host.to("cuda", non_blocking=True)
         out = self.search(q)
-        res = (out["scores"].to("cpu", non_blocking=True), out["ids"].to("cpu", non_blocking=True),
-               out["source"].to("cpu", non_blocking=True))
+        blk: MergeOut = out["_block"]
+        B, k, n = blk.B, blk.k, blk.B * blk.k
+        host = self._host_out.get(B)
+        if host is None:
+            host = self._host_out[B] = torch.empty(blk.host_bytes, dtype=torch.uint8).pin_memory()
+        host.copy_(blk.buf[:blk.host_bytes], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return res
+        return (host[8 * n:12 * n].view(torch.float32).view(B, k), host[:8 * n].view(torch.int64).view(B, k),
+                host[12 * n:16 * n].view(torch.int32).view(B, k))
 
 
 def place_sources(names: Sequence[str], world: int) -> Dict[str, int]:

@@ -380,3 +380,31 @@ def test_config5_sixteen_mixed_dim_sources_placed_on_two_ranks(cuda_required):
     valid = (src2 >= 0).cpu().numpy()
     want_rank = np.vectorize(lambda s: where[names[s]] if s >= 0 else -1)(src2.cpu().numpy())
     assert np.array_equal(rank2.cpu().numpy()[valid], want_rank[valid])
+
+
+def test_search_host_equals_device_search(cuda_required):
+    """The host-buffer entry point (pinned queries in, one packed copy out) returns what the device path returns."""
+    from ragroute_b200 import synthetic as syn
+    from ragroute_b200.selftest import build_small_medrag
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation
+    from ragroute_b200.router import MEDRAG_THRESHOLD
+    from ragroute_b200.workloads import make_synthetic_router
+    d, k = 768, 32
+    names, sids, corpora, _, _, centroids = build_small_medrag(n_rows=(6000, 9000), d=d)
+    router = make_synthetic_router(names, d, centroids, 3, 0)
+    sources = {}
+    for n in names:
+        ix = IndexFlatIP(d)
+        ix.add(corpora[n])
+        sources[n] = ix
+    fed = Federation(sources, k, router=router, routing="ragroute", threshold=MEDRAG_THRESHOLD)
+    for B in (1, 33, 33, 200):                                       # 33 twice: the pinned buffer is reused
+        qh = torch.from_numpy(syn.queries(B, d, sids, seed=B)).pin_memory()
+        s_h, i_h, src_h = fed.search_host(qh)
+        s_h, i_h, src_h = s_h.clone(), i_h.clone(), src_h.clone()
+        dev = fed.search(qh.cuda())
+        torch.cuda.synchronize()
+        assert torch.equal(s_h, dev["scores"].cpu()) and torch.equal(i_h, dev["ids"].cpu())
+        assert torch.equal(src_h, dev["source"].cpu())
+        assert s_h.shape == (B, k) and i_h.dtype == torch.int64 and src_h.dtype == torch.int32
