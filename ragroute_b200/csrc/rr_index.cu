@@ -1185,8 +1185,8 @@ static size_t rr_align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 //   nq > 128            decided on the device from the number of ROUTED queries (the host only knows
 //                       the batch size): <= 128 routed -> as above; more -> CTA pairs (256 queries per
 //                       pair; two 128-query single-CTA tiles would pull every corpus tile into two SMs)
-// Dimensions whose query tile does not fit TMEM + shared memory (d_pad > 768) always take the
-// swap-AB scan in passes of <= 64 queries.
+// Dimensions whose 128-query tile does not fit TMEM + shared memory (d_pad > 1024) always take the
+// swap-AB scan in passes of <= 32 / 16 queries.
 static bool rr_use_gemm_path(const rr_index* h, int64_t nq) {
     if (!rr_gemm_scan_supported(h) || h->scan_path == RR_PATH_SMALL) return false;
     if (h->scan_path == RR_PATH_GEMM || h->scan_path == RR_PATH_GEMM_PAIR) return true;

@@ -11,10 +11,11 @@
 //   * a tile of 128 queries is stationary for the whole kernel as the UMMA A operand: its
 //     first 512 dimensions live in TENSOR MEMORY (TS form of tcgen05.mma: row m of A in
 //     TMEM lane m, 2 bf16 per 32-bit column = 256 columns, written once by tcgen05.st),
-//     the remaining <= 256 dimensions in shared memory (SS form, 64 KB, loaded once by TMA).
-//     The split leaves 256 TMEM columns = TWO accumulator stages, so the epilogue of tile i
-//     runs under the MMAs of tile i+1 (with all 768 dims in TMEM only one stage fits and the
-//     tensor pipe idles ~25 % of the time waiting for the accumulator to drain);
+//     the remaining <= 512 dimensions (d_pad <= 1024) in shared memory (SS form, loaded once by
+//     TMA).  The split leaves 256 TMEM columns = TWO accumulator stages, so the epilogue of tile i
+//     runs under the MMAs of tile i+1 (with 768 dims in TMEM only one stage fits and the
+//     tensor pipe idles ~25 % of the time waiting for the accumulator to drain -- which is
+//     the layout of choice when a single query tile makes the launch HBM-bound anyway);
 //   * corpus rows stream through shared memory as the B operand, 128 rows x 64 k per
 //     16 KB TMA stage (128B swizzle), ring of 12 stages (192 KB in flight per SM); UMMA
 //     N = 128 because one tcgen05.mma costs >= 45 cycles whatever its N (measured:
@@ -52,6 +53,7 @@ constexpr int kMaxStages = 8;
 constexpr int kMaxAcc = 2;
 constexpr int kMaxATmemKc = ((int)512 - kMaxAcc * RR_GEMM_TILE_ROWS) / 32;  // 8 K-chunks = 512 dims of A in TMEM
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kMaxDpad = 1024;
 constexpr uint32_t kTmemCols = 512;
 
 struct GemmParams {
@@ -550,8 +552,9 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 }  // namespace
 
 bool rr_gemm_scan_supported(const rr_index* h) {
-    // 512 dims of the query tile in TMEM + at most 256 more in shared memory
-    return h->d_pad <= (kMaxATmemKc + 4) * RR_TC_KCHUNK;
+    // the 128-query tile lives in TMEM (up to 768 dims next to one accumulator stage, 512 next to two) and
+    // shared memory (up to 512 dims): 1024 dimensions at most
+    return h->d_pad <= kMaxDpad;
 }
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
@@ -563,6 +566,8 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
                          (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
     p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / stage_b);
+    RR_REQUIRE(p.stages >= 2, "rr_gemm_scan: d_pad=%d leaves room for %d TMA stage(s) with %d CTA(s) per query tile",
+               p.d_pad, p.stages, CG);
     const size_t smem = fixed + (size_t)p.stages * stage_b;
     static bool attr_done[64] = {};
     if (!attr_done[h->device & 63]) {
@@ -636,17 +641,20 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     p.n_tiles = (int)((h->n + kNT - 1) / kNT);
     p.num_kc = h->d_pad / RR_TC_KCHUNK;
     p.d_pad = h->d_pad;
+    // Where the stationary 128-query tile lives.  Default: 512 dims in TMEM + the rest (<= 512 dims) in shared
+    // memory, which leaves 256 TMEM columns = two accumulator stages.
     p.acc_stages = kMaxAcc;
     p.a_tmem_kc = std::min(p.num_kc, kMaxATmemKc);
     p.a_smem_kc = p.num_kc - p.a_tmem_kc;
-    if ((nq <= kQTile || max_active <= kQTile) && cta_group == 1 && h->gemm_tmem_all &&
-        p.num_kc * 32 + kNT <= (int)kTmemCols) {
-        // one query tile = the HBM-bound regime (intensity <= 128 flop/byte): the tensor pipe has slack, so the
-        // whole tile goes to TMEM with ONE accumulator stage (the MMAs of the next corpus tile wait for the
-        // epilogue's tcgen05.ld, a fraction of the tile's HBM time) and the shared memory it frees becomes
-        // two more TMA stages in flight
-        p.a_tmem_kc = p.num_kc;
-        p.a_smem_kc = 0;
+    const bool one_tile = cta_group == 1 && (nq <= kQTile || max_active <= kQTile);
+    constexpr int kTmemKcOneAcc = ((int)kTmemCols - kNT) / 32;  // 12 K-chunks = 768 dims next to ONE accumulator
+    if (one_tile && (h->gemm_tmem_all || p.num_kc > kMaxATmemKc + 4)) {
+        // one query tile = the HBM-bound regime (intensity <= 128 flop/byte): the tensor pipe has slack, so
+        // up to 768 dims go to TMEM with ONE accumulator stage (the MMAs of the next corpus tile wait for the
+        // epilogue's tcgen05.ld, a fraction of the tile's HBM time) and the shared memory that frees becomes
+        // TMA stages in flight
+        p.a_tmem_kc = std::min(p.num_kc, kTmemKcOneAcc);
+        p.a_smem_kc = p.num_kc - p.a_tmem_kc;
         p.acc_stages = 1;
     }
     p.stages = 0;

@@ -264,6 +264,41 @@ def test_gemm_path_vs_oracle(faiss, n, d, k, nq, path):
     assert np.array_equal(I, Ie) and np.array_equal(D, De), "gemm path and exact must agree bit for bit"
 
 
+@pytest.mark.parametrize("d", [832, 1000, 1024])
+def test_gemm_path_wide_rows_up_to_1024_dims(faiss, d):
+    """768 < d_pad <= 1024 (FeB4RAG's 1024-d encoders, config.py:44-58): the query tile's tail beyond
+    TMEM lives in shared memory -- 768 + 256 dims with one accumulator stage for a single query tile,
+    512 + 512 with two for CTA pairs.  Default dispatch (single CTA / pairs picked on the device), both
+    routed densities, against the oracle and bit for bit against exact mode and the swap-AB scan."""
+    k = 10
+    rng = np.random.default_rng(d)
+    xb = (rng.standard_normal((21000, d), dtype=np.float32) / np.float32(np.sqrt(d))
+          + rng.standard_normal(d).astype(np.float32) * np.float32(0.5 / np.sqrt(d)))
+    ixe = _index(faiss, xb, "exact")
+    for nq, density in ((30, 1.0), (100, 1.0), (300, 1.0), (300, 0.3), (2100, 0.7)):
+        q = rng.standard_normal((nq, d), dtype=np.float32) / np.float32(np.sqrt(d))
+        ix = _index(faiss, xb, "auto")
+        qt = torch.from_numpy(q).cuda()
+        mask = torch.from_numpy((rng.random((nq, 1)) < density).astype(np.uint8)).cuda()
+        D, I = ix.search_tensor(qt, k, mask=mask)
+        torch.cuda.synchronize()
+        D, I, m = D.cpu().numpy(), I.cpu().numpy(), mask.cpu().numpy()[:, 0].astype(bool)
+        assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data: {ix.stats()}"
+        assert (I[~m] == -1).all()
+        De, Ie = ixe.search(q, k)
+        assert np.array_equal(I[m], Ie[m]) and np.array_equal(D[m], De[m]), "auto and exact must agree bit for bit"
+        sel = np.nonzero(m)[0][:20]
+        Dr, Ir = oracle.search(q[sel], xb, k)
+        oracle.compare_topk(D[sel], I[sel], Dr, Ir, x=q[sel], xb=xb)
+    # forced CTA pairs on a small batch, and the swap-AB scan, agree too
+    q = rng.standard_normal((70, d), dtype=np.float32) / np.float32(np.sqrt(d))
+    De, Ie = ixe.search(q, k)
+    for path in (1, 3):
+        ix = _gemm_index(faiss, xb, path)
+        D, I = ix.search(q, k)
+        assert np.array_equal(I, Ie) and np.array_equal(D, De)
+
+
 def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
     """On benign MedRAG-shaped data the certificate must pass for every query (otherwise
     the exact rescan would hide a broken tensor-core kernel), for 1, 2 and 8 query tiles."""
