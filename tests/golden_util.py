@@ -2,12 +2,14 @@
 tests/golden/router_*.npz (the generating script is tests/golden/gen_golden.py;
 it ran the reference's own code for the recorded outputs)."""
 import os
+import subprocess
 
 import numpy as np
 
 from ragroute_b200 import synthetic as syn
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 class RouterCase:
@@ -41,3 +43,17 @@ class RouterCase:
     def query(self, qi: int):
         return {m: syn.hash_uniform(self.seed * 100000 + 7000 + qi * 16 + mi, (self.model_dims[m],), -0.4, 0.4)
                 for mi, m in enumerate(self.models)}
+
+
+def build_abi_check(tmp_path):
+    """gcc tests/c/abi_check.c against include/ragroute_b200.h and the in-tree library -> executable path."""
+    from ragroute_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__ as entry
+        entry.build_cuda()
+    exe = str(tmp_path / "abi_check")
+    libdir = os.path.dirname(_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(REPO, "include"),
+                    os.path.join(REPO, "tests", "c", "abi_check.c"), "-o", exe, "-L", libdir, "-lragroute_b200",
+                    "-Wl,-rpath," + libdir], check=True)
+    return exe

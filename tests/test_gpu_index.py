@@ -413,3 +413,14 @@ def test_near_duplicate_documents_are_settled_by_the_second_pass(faiss, nq, path
     sel = np.arange(0, nq, max(1, nq // 5))
     Dr, Ir = oracle.search(q[sel], xb, k)
     oracle.compare_topk(D[sel], I[sel], Dr, Ir, x=q[sel], xb=xb)
+
+
+def test_plain_c_caller_known_answers(faiss, tmp_path):
+    """tests/c/abi_check.c --compute: a C program builds a 64 x 8 index through the C ABI and checks the
+    hand-computable top-5 (ties: lower row first) in auto and exact mode."""
+    import subprocess
+    from golden_util import build_abi_check
+    exe = build_abi_check(tmp_path)
+    res = subprocess.run([exe, "--compute"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "abi_check ok (compute" in res.stdout

@@ -118,3 +118,15 @@ def test_sharded_gather_merge_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+from golden_util import build_abi_check as _build_abi_check
+
+
+def test_c_abi_is_callable_from_plain_c(tmp_path):
+    """The header compiles as C99 and the library links into a plain C program (no CUDA / torch types in
+    the boundary); without a GPU every compute entry point refuses loudly."""
+    exe = _build_abi_check(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "abi_check ok" in res.stdout
