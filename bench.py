@@ -421,12 +421,12 @@ def gpu_main(args, rows, workload):
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         t0 = time.time()
-        cqps, cms, info = run_cpu_reference(rows, B, steps=4, warmup=1,
+        cqps, cms, info = run_cpu_reference(rows, B, steps=8, warmup=1,
                                             sample_rows_total=cpu_sample_rows(args.cpu_sample_rows, B))
         cpu_baseline = {
             "value": cqps, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
             "sample": (f"{sum(info['rows_sampled'].values())} of {sum(rows.values())} rows "
-                       f"({info['row_fraction']:.4%}), batch {B}, 4 timed steps, routed pairs only "
+                       f"({info['row_fraction']:.4%}), batch {B}, 8 timed steps, routed pairs only "
                        f"(mask density {info['mask_density']:.2f}), FAISS-restated sequential scan, OpenMP over "
                        f"queries; queries/s scaled linearly in rows; {time.time() - t0:.1f}s wall"),
         }
