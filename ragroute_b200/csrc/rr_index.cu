@@ -4,12 +4,15 @@
 // Storage: two 16-bit planes per corpus (see rr_common.cuh) = 4 bytes / element,
 // the same footprint as FAISS' fp32 rows, of which a scan streams only 2.
 //
-// Search pipeline for a chunk of queries (all on one stream, no host sync):
-//   compact   (large batch) routed queries to the front, so unrouted pairs cost nothing
+// Search pipeline for a chunk of queries against S sources (all on one stream, no host sync; every
+// stage but the scans is ONE launch for all sources -- rr_federation_search; index.search is S = 1):
+//   begin     zero the control blocks; (large batch) compact the routed queries to the front, so
+//             unrouted pairs cost nothing
 //   prep      fp32 queries -> bf16 rows (+ L2 norms for the certificate)
-//   scan      <= 48 queries: rr_scan_tc.cu (swap-AB, per-warp top-16 lists);
-//             more: rr_scan_gemm.cu (queries stationary in TMEM, per-query top-32 lists,
-//             CTA pairs above 256 queries)
+//   scan      per source, chained by programmatic dependent launch.  <= 24 queries: rr_scan_tc.cu
+//             (swap-AB, per-warp top-16 lists); more: rr_scan_gemm.cu (queries stationary in TMEM,
+//             per-query top-32 lists; single CTAs up to 128 ROUTED queries, CTA pairs above --
+//             decided on the device)
 //   finalize  per query: radix-select the kprime best bf16 candidates, rescore
 //             them exactly (fp32 rows rebuilt from the planes, fp64 accumulate),
 //             sort, and CERTIFY: every row that is not a candidate has bf16 score

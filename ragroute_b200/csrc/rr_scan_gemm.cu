@@ -6,7 +6,7 @@
 //
 // With B >= 128 queries the arithmetic intensity over the bf16 plane (B flop/byte)
 // approaches / exceeds the ridge (~215), so the corpus must be read from HBM once per
-// chunk of up to 1024 queries and every byte brought into an SM must be used against as
+// chunk of up to 2048 queries and every byte brought into an SM must be used against as
 // many queries as possible:
 //   * a tile of 128 queries is stationary for the whole kernel as the UMMA A operand: its
 //     first 512 dimensions live in TENSOR MEMORY (TS form of tcgen05.mma: row m of A in
