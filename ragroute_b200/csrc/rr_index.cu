@@ -538,12 +538,26 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
             if (tid < 256) hist[tid] = 0;
             __syncthreads();
             const unsigned long long prefix = s_prefix, mask = s_mask;
-            for (int i = tid; i < n_cand; i += blockDim.x) {
-                const uint32_t r = cr[i];
-                if (r == RR_NO_ROW) continue;
-                unsigned long long key = rr_float_key(cs[i]);
-                if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
-                if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xFFull], 1u);
+            // warp-aggregated counting: candidate scores cluster (same sign and exponent), so in the leading
+            // passes nearly every lane hits the same bin and plain shared-memory atomics would serialise
+            for (int i0 = 0; i0 < n_cand; i0 += n_threads) {
+                const int i = i0 + tid;
+                uint32_t digit = 0;
+                bool in = false;
+                if (i < n_cand) {
+                    const uint32_t r = cr[i];
+                    if (r != RR_NO_ROW) {
+                        unsigned long long key = rr_float_key(cs[i]);
+                        if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
+                        in = (key & mask) == prefix;
+                        digit = (uint32_t)((key >> shift) & 0xFFull);
+                    }
+                }
+                const unsigned live = __ballot_sync(RR_FULL, in);
+                if (in) {
+                    const unsigned peers = __match_any_sync(live, digit);
+                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+                }
             }
             __syncthreads();
             if (w == 0) {
@@ -678,27 +692,16 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
         __syncthreads();
     }
 
-    // bitonic sort of sel[0, kp_pad) into ranking order (score desc, row asc)
-    for (int ksz = 2; ksz <= kp_pad; ksz <<= 1) {
-        for (int j = ksz >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < kp_pad; i += blockDim.x) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const bool first_low = (i & ksz) == 0;
-                    const float s1 = sel_s[i], s2 = sel_s[p];
-                    const uint32_t r1 = sel_r[i], r2 = sel_r[p];
-                    const bool swap = first_low ? rr_before(s2, r2, s1, r1) : rr_before(s1, r1, s2, r2);
-                    if (swap) {
-                        sel_s[i] = s2;
-                        sel_r[i] = r2;
-                        sel_s[p] = s1;
-                        sel_r[p] = r1;
-                    }
-                }
-            }
-            __syncthreads();
+    // sort sel[0, kp_pad) into ranking order (score desc, row asc): one warp, entries in registers
+    if (w == 0) {
+        switch (kp_pad >> 5) {
+            case 1: rr_warp_sort_smem<1>(sel_s, sel_r, lane); break;
+            case 2: rr_warp_sort_smem<2>(sel_s, sel_r, lane); break;
+            case 4: rr_warp_sort_smem<4>(sel_s, sel_r, lane); break;
+            default: rr_warp_sort_smem<8>(sel_s, sel_r, lane); break;  // RR_FIN_MAXSEL = 256
         }
     }
+    __syncthreads();
 
     bool pass = true;
     float theta = RR_NEG_INF;  // second-pass threshold if the certificate fails
@@ -1011,6 +1014,7 @@ extern "C" int rr_index_destroy(rr_index_t* h) {
     cudaFree(h->d_nfail_total);
     cudaFree(h->scratch);
     cudaFree(h->stage);
+    if (h->pin) cudaFreeHost(h->pin);
     delete h;
     return RR_OK;
 }
@@ -1328,7 +1332,14 @@ static int rr_prof_end(rr_index* h, cudaStream_t stream, bool on, int launches) 
 
 // One chunk of queries against S <= RR_FED_MAX sources (all on one device and stream): the scans are one
 // launch per source, every other stage is one launch for all of them.
-static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t stream) {
+// `phases`: RR_PHASE_FIRST = begin, prep, the tensor-core scans and their finalize (results of every query
+// whose certificate held are final after it, and ctl->n_fail counts the others); RR_PHASE_REPAIR = second
+// pass, exact scan and their finalizes.  Device callers run both back to back (the repair launches exit at
+// once when nothing failed); a host caller that synchronises anyway runs the second only when needed.
+constexpr int RR_PHASE_FIRST = 1, RR_PHASE_REPAIR = 2, RR_PHASE_ALL = 3;
+
+static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t stream, int phases = RR_PHASE_ALL) {
+    const bool do_first = (phases & RR_PHASE_FIRST) != 0, do_repair = (phases & RR_PHASE_REPAIR) != 0;
     int max_nq_pad = 0, max_nq_pad2 = 0, max_dpad = 0;
     size_t max_ex_smem = 0;
     bool any_first = false, any_pass2 = false, any_rows = false;
@@ -1392,11 +1403,13 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         a.exact_all = (p.use_tc || p.use_gemm) ? 0 : 1;
         a.compact = p.use_gemm ? 1 : 0;
     }
-    rr_begin_chunk_kernel<<<S, 1024, 0, stream>>>(pa);
-    RR_CUDA_CHECK(cudaGetLastError());
-    rr_prep_queries_kernel<<<dim3((unsigned)max_nq_pad, (unsigned)S), 128, 0, stream>>>(pa);
-    RR_CUDA_CHECK(cudaGetLastError());
-    rr_count_launch(2);
+    if (do_first) {
+        rr_begin_chunk_kernel<<<S, 1024, 0, stream>>>(pa);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_prep_queries_kernel<<<dim3((unsigned)max_nq_pad, (unsigned)S), 128, 0, stream>>>(pa);
+        RR_CUDA_CHECK(cudaGetLastError());
+        rr_count_launch(2);
+    }
 
     rr_multi<rr_finalize_args> fa;
     memset(&fa, 0, sizeof(fa));
@@ -1435,6 +1448,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
     // ---- first pass: bf16 tensor-core scan of every source, then one finalize for all of them.  The scans
     // are chained by programmatic dependent launch (they touch disjoint memory): no gap and no idle SMs
     // between them.  Profiling brackets the whole chain with one event pair.
+    if (do_first) {
     rr_index* hprof = nullptr;
     for (int s = 0; s < S && !hprof; ++s)
         if ((plans[s].use_gemm || plans[s].use_tc) && plans[s].h->profile) hprof = plans[s].h;
@@ -1486,6 +1500,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         RR_CUDA_CHECK(cudaGetLastError());
         rr_count_launch(1);
     }
+    }  // do_first
+    if (!do_repair) return RR_OK;
 
     // ---- second pass over the queries whose certificate failed: the tensor-core scan again, this time
     // reporting every row above a per-query threshold that provably keeps the whole exact top-k; then
@@ -1729,25 +1745,60 @@ extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t 
                                     float* D_host, int64_t* I_host) {
     RR_REQUIRE(h != nullptr, "rr_index_search_host: NULL handle");
     RR_REQUIRE(nq >= 0 && k > 0, "rr_index_search_host: bad nq / k");
+    if (k > RR_MAX_K) {
+        rr_set_error("rr_index_search: k=%d > RR_MAX_K=%d is not implemented", k, RR_MAX_K);
+        return RR_ERR_UNSUPPORTED;
+    }
     if (nq == 0) return RR_OK;
     RR_REQUIRE(q_host && D_host && I_host, "rr_index_search_host: NULL buffer");
     rr_device_guard g(h->device);
+    // device staging: [ queries | D | I | control block ]; the last three leave in ONE copy
     const size_t qb = rr_align_up((size_t)nq * h->d * sizeof(float), 256);
     const size_t db = rr_align_up((size_t)nq * k * sizeof(float), 256);
-    const size_t ib = (size_t)nq * k * sizeof(int64_t);
-    int rc = rr_grow((void**)&h->stage, &h->stage_bytes, qb + db + ib);
+    const size_t ib = rr_align_up((size_t)nq * k * sizeof(int64_t), 256);
+    const size_t out_b = db + ib + sizeof(rr_chunk_ctl);
+    int rc = rr_grow((void**)&h->stage, &h->stage_bytes, qb + out_b);
     if (rc != RR_OK) return rc;
+    if (h->pin_bytes < out_b) {
+        if (h->pin) cudaFreeHost(h->pin);
+        h->pin = nullptr;
+        h->pin_bytes = 0;
+        RR_CUDA_CHECK(cudaHostAlloc(&h->pin, out_b + out_b / 4, cudaHostAllocDefault));
+        h->pin_bytes = out_b + out_b / 4;
+    }
     char* base = (char*)h->stage;
     float* q_dev = (float*)base;
     float* D_dev = (float*)(base + qb);
     int64_t* I_dev = (int64_t*)(base + qb + db);
+    rr_chunk_ctl* ctl_dev = (rr_chunk_ctl*)(base + qb + db + ib);
     cudaStream_t stream = 0;
     RR_CUDA_CHECK(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, stream));
-    rc = rr_index_search(h, q_dev, nq, k, D_dev, I_dev, stream);
-    if (rc != RR_OK) return rc;
-    RR_CUDA_CHECK(cudaMemcpyAsync(D_host, D_dev, (size_t)nq * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    RR_CUDA_CHECK(cudaMemcpyAsync(I_host, I_dev, ib, cudaMemcpyDeviceToHost, stream));
-    RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (nq <= rr_chunk_size(h, nq)) {
+        // One chunk -- the reference's call (nq = 1, data_source.py:186).  This caller waits for its result
+        // anyway, so it runs the first pass, looks at the count of failed certificates that comes back with
+        // the results, and launches the repair stages only when there is something to repair.
+        rr_chunk_plan plan;
+        rc = rr_plan_chunk(h, q_dev, (int)nq, nullptr, 0, D_dev, I_dev, k, stream, &plan);
+        if (rc != RR_OK) return rc;
+        plan.ctl = ctl_dev;
+        for (int phase = RR_PHASE_FIRST; phase <= RR_PHASE_REPAIR; ++phase) {
+            rc = rr_run_chunk(&plan, 1, (int)nq, k, stream, phase);
+            if (rc != RR_OK) return rc;
+            RR_CUDA_CHECK(cudaMemcpyAsync(h->pin, D_dev, out_b, cudaMemcpyDeviceToHost, stream));
+            RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+            const rr_chunk_ctl* ctl_host = (const rr_chunk_ctl*)((const char*)h->pin + db + ib);
+            if (ctl_host->n_fail == 0) break;  // every certificate held: the results are final
+        }
+        h->stats.searches += 1;
+        h->stats.queries += nq;
+    } else {
+        rc = rr_index_search(h, q_dev, nq, k, D_dev, I_dev, stream);
+        if (rc != RR_OK) return rc;
+        RR_CUDA_CHECK(cudaMemcpyAsync(h->pin, D_dev, db + ib, cudaMemcpyDeviceToHost, stream));
+        RR_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+    memcpy(D_host, h->pin, (size_t)nq * k * sizeof(float));
+    memcpy(I_host, (const char*)h->pin + db, (size_t)nq * k * sizeof(int64_t));
     return RR_OK;
 }
 

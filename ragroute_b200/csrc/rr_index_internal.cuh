@@ -47,6 +47,8 @@ struct rr_index {
     size_t scratch_bytes = 0;
     float* stage = nullptr;  // host->device staging for add / search_host
     size_t stage_bytes = 0;
+    void* pin = nullptr;     // pinned host mirror of search_host's result block
+    size_t pin_bytes = 0;
 
     // TMA descriptor of the hi plane (rebuilt when hi / n change)
     alignas(64) CUtensorMap tmap_hi;

@@ -273,13 +273,32 @@ rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                 acc_phase ^= 1u;
             }
         }
-        // publish this warp's lists: [query][list = cta*4 + ew][kDepth]
-        const int64_t list = (int64_t)blockIdx.x * RR_TC_EPI_WARPS + ew;
-        for (int i = lane; i < p.nq_tile * kDepth; i += 32) {
-            const int q = i / kDepth, e = i - q * kDepth;
-            const int64_t o = (int64_t)q * p.cand_stride + list * kDepth + e;
-            p.cand_s[o] = ls_w[i];
-            p.cand_r[o] = lr_w[i];
+        // Fold the four warps' lists of every query into ONE list per CTA (the best kDepth of the union: any
+        // row dropped here or earlier scores <= the merged tail, so the list keeps its meaning) and publish
+        // it: [query][list = cta][kDepth].  A quarter of the candidates for the finalize to select from.
+        asm volatile("bar.sync 1, %0;" ::"n"(RR_TC_EPI_WARPS * 32) : "memory");  // the 4 epilogue warps only
+        for (int q = ew; q < p.nq_tile; q += RR_TC_EPI_WARPS) {
+            float es = RR_NEG_INF;
+            uint32_t er = RR_NO_ROW;
+            if (lane < kDepth) {
+                es = ls[q * kDepth + lane];
+                er = lr[q * kDepth + lane];
+            }
+#pragma unroll
+            for (int w2 = 1; w2 < RR_TC_EPI_WARPS; ++w2) {
+                float cs = RR_NEG_INF;
+                uint32_t cr = RR_NO_ROW;
+                if (lane < kDepth) {
+                    cs = ls[(w2 * QT + q) * kDepth + lane];
+                    cr = lr[(w2 * QT + q) * kDepth + lane];
+                }
+                rr_list_merge_sorted(es, er, cs, cr, kDepth, lane);
+            }
+            if (lane < kDepth) {
+                const int64_t o = (int64_t)q * p.cand_stride + (int64_t)blockIdx.x * kDepth + lane;
+                p.cand_s[o] = es;
+                p.cand_r[o] = er;
+            }
         }
     }
 
@@ -343,7 +362,7 @@ int rr_tc_scan_qtile(const rr_index* h) {
     return 0;
 }
 
-int rr_tc_scan_num_lists(const rr_index* h) { return h->sm_count * RR_TC_EPI_WARPS; }
+int rr_tc_scan_num_lists(const rr_index* h) { return h->sm_count; }
 
 int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_total, int q_row0, int nq_tile,
                       const uint8_t* active_dev, const int* any_active_dev, float* cand_s, uint32_t* cand_r,
@@ -377,7 +396,7 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
     p.cand_r = cand_r;
     p.cand_stride = cand_stride;
     const int grid = std::min(h->sm_count, p.n_tiles);
-    *n_lists_out = grid * RR_TC_EPI_WARPS;
+    *n_lists_out = grid;  // one merged list per CTA
     switch (qt) {
         case 64: return launch_qt<64>(h, tq, p, grid, pl.bytes, chain, stream);
         case 32: return launch_qt<32>(h, tq, p, grid, pl.bytes, chain, stream);

@@ -76,3 +76,49 @@ __device__ __forceinline__ void rr_list_merge_sorted(float& es, uint32_t& er, fl
         er = RR_NO_ROW;
     }
 }
+
+// Sort 32 * E entries held in shared memory into ranking order with ONE warp: entry lane * E + e lives in
+// register e of its lane; stages whose partner distance is below E swap registers, the others exchange
+// between lanes (no block-wide barriers: a 128-entry sort is 28 stages of ~30 instructions).
+template <int E>
+__device__ __noinline__ void rr_warp_sort_smem(float* s, uint32_t* r, int lane) {
+    float vs[E];
+    uint32_t vr[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        vs[e] = s[lane * E + e];
+        vr[e] = r[lane * E + e];
+    }
+#pragma unroll
+    for (int k = 2; k <= 32 * E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                const bool first_low = (((lane * E + e) & k) == 0);  // the lower index keeps the first-ranked
+                if (j < E) {
+                    if ((e & j) == 0) {
+                        const int e2 = e | j;
+                        const bool swap = first_low ? rr_before(vs[e2], vr[e2], vs[e], vr[e])
+                                                    : rr_before(vs[e], vr[e], vs[e2], vr[e2]);
+                        if (swap) {
+                            const float ts = vs[e];
+                            const uint32_t tr = vr[e];
+                            vs[e] = vs[e2];
+                            vr[e] = vr[e2];
+                            vs[e2] = ts;
+                            vr[e2] = tr;
+                        }
+                    }
+                } else {
+                    rr_cmpxchg(vs[e], vr[e], j / E, first_low, lane);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        s[lane * E + e] = vs[e];
+        r[lane * E + e] = vr[e];
+    }
+}
