@@ -9,9 +9,10 @@ run() { # name, pytest args...
   echo "$name exit=$? $(tail -1 gpurun_out/$name.log)"
 }
 run router_rerank tests/test_gpu_router_rerank.py
-run index_exact tests/test_gpu_index.py -k "exact or reconstruct or normalize or errors or offset"
+run index_exact tests/test_gpu_index.py -k "(exact or reconstruct or normalize or errors or offset) and not fuzz"
 run index_tcscan tests/test_gpu_index.py -k "tc_scan_candidates"
-run index_auto tests/test_gpu_index.py -k "not exact and not tc_scan_candidates and not reconstruct and not normalize and not errors and not offset and not gemm and not config0 and not multi_million and not near_duplicate"
+run index_auto tests/test_gpu_index.py -k "not exact and not tc_scan_candidates and not reconstruct and not normalize and not errors and not offset and not gemm and not config0 and not multi_million and not near_duplicate and not fuzz"
 run index_gemm tests/test_gpu_index.py -k "gemm"
 run index_sizes tests/test_gpu_index.py -k "config0 or multi_million or near_duplicate"
+run index_fuzz tests/test_gpu_index.py -k "fuzz"
 run federation tests/test_gpu_federation.py

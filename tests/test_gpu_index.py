@@ -424,3 +424,60 @@ def test_plain_c_caller_known_answers(faiss, tmp_path):
     res = subprocess.run([exe, "--compute"], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "abi_check ok (compute" in res.stdout
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RR_FUZZ_CASES", "36"))))
+def test_fuzz_auto_equals_exact(faiss, seed):
+    """Randomised shapes through the default dispatch (swap-AB scan, queries in TMEM on single CTAs / CTA
+    pairs picked on the device, chained launches, second pass) against the exact-scan mode of the same
+    library, which the oracle pins: ids and scores bit for bit, padding for unrouted queries, id offsets.
+    The exact mode is one simple kernel; agreement on ragged sizes, duplicates and partial tiles is the
+    property that the tensor-core machinery changes HOW FAST, never WHAT."""
+    rng = np.random.default_rng(9000 + seed)
+    d = int(rng.choice([8, 64, 100, 384, 512, 640, 768, 832, 1024]))
+    n = int(np.exp(rng.uniform(np.log(1), np.log(40000))))
+    nq = int(np.exp(rng.uniform(np.log(1), np.log(2300))))
+    nq = max(1, min(nq, int(3e7 // max(n, 1))))
+    k = int(rng.integers(1, 33))
+    density = float(rng.choice([0.0, 0.05, 0.3, 0.7, 1.0]))
+    offset = int(rng.choice([0, 12345, 1 << 33]))
+    mu = rng.standard_normal(d).astype(np.float32) * np.float32(0.5 / np.sqrt(d))
+    xb = rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d)) + mu
+    flavour = seed % 4
+    if flavour == 1 and n > 8:                       # exact duplicates (ties broken by row)
+        xb[rng.integers(0, n, size=n // 3)] = xb[rng.integers(0, n)]
+    elif flavour == 2 and n > 8:                     # a run of near-duplicates: certificates fail
+        j = int(rng.integers(0, n))
+        m = min(n, 300)
+        lo = max(0, min(j, n - m))
+        xb[lo:lo + m] = xb[j] * (1 + 1e-4 * rng.standard_normal((m, 1)).astype(np.float32))
+    elif flavour == 3:                               # small integers: exact in bf16, many equal scores
+        xb = rng.integers(-3, 4, size=(n, d)).astype(np.float32)
+    q = rng.standard_normal((nq, d), dtype=np.float32) / np.float32(np.sqrt(d)) + mu
+    if flavour == 3:
+        q = rng.integers(-2, 3, size=(nq, d)).astype(np.float32)
+    mask = (rng.random((nq, 1)) < density).astype(np.uint8)
+    res = {}
+    for mode in ("auto", "exact"):
+        ix = _index(faiss, xb, mode)
+        ix.set_id_offset(offset)
+        D, I = ix.search_tensor(torch.from_numpy(q).cuda(), k, mask=torch.from_numpy(mask).cuda())
+        torch.cuda.synchronize()
+        res[mode] = (D.cpu().numpy(), I.cpu().numpy())
+    (Da, Ia), (De, Ie) = res["auto"], res["exact"]
+    tag = f"seed={seed} n={n} d={d} nq={nq} k={k} density={density} flavour={flavour}"
+    assert np.array_equal(Ia, Ie), tag
+    assert np.array_equal(Da, De), tag
+    m = mask[:, 0].astype(bool)
+    assert (Ia[~m] == -1).all() and (Da[~m] == -FLT_MAX).all(), tag
+    if m.any():
+        kk = min(k, n)
+        assert (Ia[m][:, :kk] >= offset).all() and (Ia[m][:, :kk] < offset + n).all(), tag
+        assert (Ia[m][:, kk:] == -1).all(), tag
+        if n > 1:
+            assert (np.diff(Da[m][:, :kk], axis=1) <= 0).all(), tag      # descending
+    # the exact mode itself against the oracle on a few routed queries
+    sel = np.nonzero(m)[0][:4]
+    if len(sel):
+        Dr, Ir = oracle.search_seq(q[sel], xb, k)
+        oracle.compare_topk(De[sel], np.where(Ie[sel] >= 0, Ie[sel] - offset, -1), Dr, Ir, x=q[sel], xb=xb)
