@@ -130,3 +130,31 @@ def test_c_abi_is_callable_from_plain_c(tmp_path):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "abi_check ok" in res.stdout
+
+
+def test_packed_lists_merge_out_layout_and_placement():
+    """The byte blocks the step moves around: views must tile their block exactly (16-byte aligned parts, no
+    overlap), because the merge kernel and the single device-to-host copy address them by offset."""
+    from ragroute_b200.federation import MergeOut, PackedLists, place_sources
+    for B, L, W in ((5, 12, 3), (1, 128, 1), (7, 130, 2), (64, 128, 8)):
+        pl = PackedLists(B, L, "cpu", n_blocks=W)
+        assert pl.n_scores % 16 == 0 and pl.block_bytes % 16 == 0 and pl.buf.numel() == W * pl.block_bytes
+        pl.buf.fill_(0)
+        for r in range(W):
+            pl.scores(r).fill_(float(r + 1))
+            pl.ids(r).fill_(-(r + 1))
+        for r in range(W):
+            assert (pl.scores(r) == float(r + 1)).all() and (pl.ids(r) == -(r + 1)).all()
+            assert pl.scores(r).data_ptr() == pl.buf.data_ptr() + r * pl.block_bytes
+            assert pl.ids(r).data_ptr() == pl.buf.data_ptr() + r * pl.block_bytes + pl.n_scores
+            assert pl.ids(r).data_ptr() % 8 == 0
+    mo = MergeOut(3, 10, "cpu")
+    n = 30
+    assert mo.buf.numel() == 24 * n and mo.host_bytes == 16 * n
+    ptrs = [mo.ids.data_ptr(), mo.scores.data_ptr(), mo.source.data_ptr(), mo.rank.data_ptr(), mo.pos.data_ptr()]
+    base = mo.buf.data_ptr()
+    assert [p - base for p in ptrs] == [0, 8 * n, 12 * n, 16 * n, 20 * n]
+    names = [f"s{i}" for i in range(13)]
+    where = place_sources(names, 8)
+    assert [where[n_] for n_ in names] == [i % 8 for i in range(13)]
+    assert set(place_sources(names, 1).values()) == {0}
