@@ -128,6 +128,14 @@ int rr_federation_search(rr_index_t* const* idx, int n_sources, const float* con
  * convention: numpy in, numpy out). */
 int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t nq, int k, float* D_host,
                          int64_t* I_host);
+/* The same with flags: RR_SEARCH_NORMALIZE_L2 = faiss.normalize_L2(x) followed by index.search(x, k)
+ * (retrieve_docs_wikipedia, data_source.py:199-203) as ONE host round trip: the queries are L2-normalised
+ * on the device before the scan.  q_out_host (or NULL) receives the queries as searched (normalised),
+ * which is what the reference's in-place normalize_L2 leaves in its array.  Both host calls run on a
+ * stream owned by the handle (not the legacy default stream). */
+#define RR_SEARCH_NORMALIZE_L2 1
+int rr_index_search_host_ex(rr_index_t* h, const float* q_host, int64_t nq, int k, int flags, float* D_host,
+                            int64_t* I_host, float* q_out_host);
 
 typedef struct rr_index_stats {
     int64_t searches;          /* search calls since creation                    */
@@ -140,7 +148,8 @@ typedef struct rr_index_stats {
     int64_t scan_flops_total;  /* algorithmic flops: 2 * routed queries * rows * d_pad */
     int64_t exact_scans;       /* of exact_rescans: queries that needed the fp64 exact scan */
 } rr_index_stats;
-/* Synchronises the recorded events; resets the timing fields when reset != 0. */
+/* Synchronises the recorded events; reset != 0 clears the timing fields and the certificate-failure
+ * counters (exact_rescans, exact_scans) after reading them; searches / queries stay cumulative. */
 int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset);
 
 /* Testing hook: run ONLY the bf16 tcgen05 scan for nq <= rr_index_tc_qtile(h)
@@ -202,8 +211,10 @@ int rr_merge_topk(const float* s_dev, const int64_t* id_dev, int64_t B, int L, i
  * g * seg_len + j, so the result equals rr_merge_topk over the concatenation [B, n_seg * seg_len].
  *   list_len > 0: every block holds seg_len / list_len per-source lists of list_len entries (what
  *   rr_federation_search writes); then osrc [B, k] = list (source) index inside the block and
- *   orank [B, k] = block (rank) index of each winner, -1 in unused slots.  Any of opos / osrc / orank
- *   may be NULL.  n_seg * seg_len <= RR_MERGE_MAX_L. */
+ *   orank [B, k] = block (rank) index of each winner, -1 in unused slots, and EQUAL scores are ordered
+ *   by (source index, id, position) instead of position alone -- independent of how rows were sharded
+ *   over the blocks, so the sharded merge equals the unsharded one bit for bit even with ties.
+ *   Any of opos / osrc / orank may be NULL.  n_seg * seg_len <= RR_MERGE_MAX_L. */
 int rr_merge_topk_segments(const float* s_dev, const int64_t* id_dev, int64_t B, int n_seg, int seg_len,
                            int64_t seg_stride_s, int64_t seg_stride_id, int k, int descending,
                            int list_len, float* os_dev, int64_t* oid_dev, int32_t* opos_dev,

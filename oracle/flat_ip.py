@@ -64,6 +64,12 @@ def _load():
             fn = getattr(lib, name)
             fn.argtypes = [f32p, f32p, i64, i64, i64, i64, f32p, i64p, ctypes.c_int]
             fn.restype = ctypes.c_int
+        lib.ref_heap_begin.argtypes = [i64, i64, f32p, i64p]
+        lib.ref_heap_begin.restype = ctypes.c_int
+        lib.ref_heap_add_results.argtypes = [f32p, i64, i64, i64, i64, i64, f32p, i64p, ctypes.c_int]
+        lib.ref_heap_add_results.restype = ctypes.c_int
+        lib.ref_heap_end.argtypes = [i64, i64, f32p, i64p]
+        lib.ref_heap_end.restype = ctypes.c_int
         lib.ref_flat_ip_scores_f64.argtypes = [f32p, f32p, i64, i64, f64p]
         lib.ref_flat_ip_scores_f64.restype = ctypes.c_int
         lib.ref_normalize_L2.argtypes = [f32p, i64, i64]
@@ -103,10 +109,11 @@ def search_seq(x, xb, k, n_threads: int = 0, row_parallel: bool = False):
 
 
 def _heap_add_block(D, I, ip_block, j0):
-    """HeapResultHandler::add_results for one corpus block, vectorised: keeping the
-    running top-k under "replace the minimum on strict >" is the same set as the
-    k best by (score desc, arrival order asc) -- equal scores never displace an
-    earlier row.  ip_block: [nq_blk, nb_blk] fp32."""
+    """HeapResultHandler::add_results for one corpus block, vectorised in numpy (kept as the
+    independent cross-check of the C heap pass: tests/test_oracle_flat_ip.py): keeping the
+    running top-k under "replace the minimum on strict >" gives the k best scores; an equal
+    score never displaces an earlier row, but WHICH of several rows tied at the k-th score is
+    evicted by a better one depends on the heap's shape -- here the latest.  ip_block: [nq_blk, nb_blk] fp32."""
     k = D.shape[1]
     nq_blk, nb_blk = ip_block.shape
     ids = np.arange(j0, j0 + nb_blk, dtype=np.int64)
@@ -118,20 +125,40 @@ def _heap_add_block(D, I, ip_block, j0):
     I[:] = np.take_along_axis(cat_i, order, axis=1)
 
 
-def search_blas(x, xb, k):
-    """FAISS nq>=20 branch: blocked sgemm + heap add_results."""
+def search_blas(x, xb, k, n_threads: int = 0, numpy_heap: bool = False):
+    """FAISS nq>=20 branch: blocked sgemm (numpy -> OpenBLAS, all cores) + the C heap pass
+    ``add_results`` per block (OpenMP over queries, as FAISS).  ``numpy_heap=True`` runs the
+    vectorised numpy restatement of the heap pass instead (slow; cross-check only).
+
+    Within a query the result SET equals search_seq's; the order of equal scores inside the
+    final list follows heap_reorder in both."""
+    lib = _load()
     x, xb = _check(x, xb)
     nq, _ = x.shape
     nb = xb.shape[0]
-    D = np.full((nq, k), -FLT_MAX, dtype=np.float32)
-    I = np.full((nq, k), -1, dtype=np.int64)
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    i64p = ctypes.POINTER(ctypes.c_int64)
+    if numpy_heap:
+        D.fill(-FLT_MAX)
+        I.fill(-1)
+    else:
+        lib.ref_heap_begin(nq, k, _f32(D), I.ctypes.data_as(i64p))
+    ip_buf = np.empty((min(nq, BLAS_QUERY_BS), BLAS_DB_BS), dtype=np.float32)
     for i0 in range(0, nq, BLAS_QUERY_BS):
         i1 = min(nq, i0 + BLAS_QUERY_BS)
         Db, Ib = D[i0:i1], I[i0:i1]
         for j0 in range(0, nb, BLAS_DB_BS):
             j1 = min(nb, j0 + BLAS_DB_BS)
-            ip = x[i0:i1] @ xb[j0:j1].T  # sgemm_
-            _heap_add_block(Db, Ib, ip.astype(np.float32, copy=False), j0)
+            ip = ip_buf[:i1 - i0, :j1 - j0]
+            np.matmul(x[i0:i1], xb[j0:j1].T, out=ip)  # sgemm_
+            if numpy_heap:
+                _heap_add_block(Db, Ib, ip, j0)
+            else:
+                lib.ref_heap_add_results(_f32(ip_buf), i1 - i0, j1 - j0, BLAS_DB_BS, j0, k, _f32(Db),
+                                         Ib.ctypes.data_as(i64p), int(n_threads))
+    if not numpy_heap:
+        lib.ref_heap_end(nq, k, _f32(D), I.ctypes.data_as(i64p))
     return D, I
 
 
@@ -140,7 +167,7 @@ def search(x, xb, k, n_threads: int = 0):
     x, xb = _check(x, xb)
     if x.shape[0] < BLAS_THRESHOLD:
         return search_seq(x, xb, k, n_threads)
-    return search_blas(x, xb, k)
+    return search_blas(x, xb, k, n_threads)
 
 
 def normalize_L2(x):

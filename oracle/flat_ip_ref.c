@@ -184,6 +184,57 @@ int ref_flat_ip_search_seq(const float* x, const float* xb, int64_t nq, int64_t 
 }
 
 /*
+ * The nq >= 20 branch (faiss/utils/distances.cpp, exhaustive_inner_product_blas): FAISS multiplies
+ * query blocks of 4096 by corpus blocks of 1024 with sgemm_ and hands every block of scores to
+ * HeapResultHandler::add_results(j0, j1, ip_block): "#pragma omp parallel for" over the queries of
+ * the block, one pass over the row of scores with the same strict "score > heap_top" rule as above.
+ * The sgemm itself is the caller's (oracle/flat_ip.py: numpy / OpenBLAS); these two functions are
+ * the heap side.  D / I hold the running heaps between blocks (heapified to (-FLT_MAX, -1) by
+ * ref_heap_begin, reordered to descending score by ref_heap_end).
+ *   ip [nq, ld] fp32 scores of rows j0 .. j0 + nb_blk of the corpus.
+ */
+int ref_heap_begin(int64_t nq, int64_t k, float* D, int64_t* I) {
+    if (k <= 0 || nq < 0) return -1;
+    for (int64_t i = 0; i < nq * k; ++i) {
+        D[i] = -FLT_MAX;
+        I[i] = -1;
+    }
+    return 0;
+}
+
+int ref_heap_add_results(const float* ip, int64_t nq, int64_t nb_blk, int64_t ld, int64_t j0, int64_t k,
+                         float* D, int64_t* I, int n_threads) {
+    if (k <= 0 || nq < 0 || nb_blk < 0 || ld < nb_blk) return -1;
+#ifdef _OPENMP
+    int nt = n_threads > 0 ? n_threads : omp_get_max_threads();
+#pragma omp parallel for num_threads(nt) schedule(static)
+#endif
+    for (int64_t i = 0; i < nq; ++i) {
+        float* simi = D + i * k;
+        int64_t* idxi = I + i * k;
+        const float* row = ip + i * ld;
+        float thresh = simi[0];
+        for (int64_t j = 0; j < nb_blk; ++j) {
+            const float dis = row[j];
+            if (thresh < dis) { /* CMin::cmp(threshold, dis): strict */
+                ref_minheap_replace_top((size_t)k, simi, idxi, dis, j0 + j);
+                thresh = simi[0];
+            }
+        }
+    }
+    return 0;
+}
+
+int ref_heap_end(int64_t nq, int64_t k, float* D, int64_t* I) {
+    if (k <= 0 || nq < 0) return -1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int64_t i = 0; i < nq; ++i) ref_minheap_reorder((size_t)k, D + i * k, I + i * k);
+    return 0;
+}
+
+/*
  * Row-parallel variant used ONLY as the multi-core CPU baseline in bench.py:
  * the same dot product and the same heap rule, but the N rows of one query are
  * split over threads (FAISS would not do this for nq < 20) and the per-thread

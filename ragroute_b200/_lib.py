@@ -18,6 +18,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ragroute_b200.h")
 RR_MODE_AUTO = 0
 RR_MODE_EXACT = 1
 RR_MAX_K = 32
+RR_SEARCH_NORMALIZE_L2 = 1
 RR_MERGE_MAX_L = 4096
 
 _lib = None
@@ -54,6 +55,7 @@ _SIGNATURES = {
     "rr_index_search_masked": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64, _P, _P, _P]),
     "rr_index_search_ex": (c_int, [c_void_p, _P, c_int64, c_int, _P, c_int64, _P, _P, c_int64, _P]),
     "rr_index_search_host": (c_int, [c_void_p, _P, c_int64, c_int, _P, _P]),
+    "rr_index_search_host_ex": (c_int, [c_void_p, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "rr_federation_search": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int64, c_int, _P, c_int64, _P, _P,
                                      c_int64, _P]),
     "rr_index_get_stats": (c_int, [c_void_p, POINTER(IndexStats), c_int]),

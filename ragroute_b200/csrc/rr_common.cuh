@@ -46,6 +46,7 @@ struct rr_device_guard {
 int rr_check_device_arch(int device);  // RR_OK iff compute capability 10.x
 void rr_count_launch(int n);            // process-wide count of this library's kernel launches
 
+constexpr int RR_MAX_DEVICES = 64;  // per-device one-time setup flags
 constexpr float RR_NEG_INF = -__builtin_huge_valf();
 constexpr uint32_t RR_NO_ROW = 0xFFFFFFFFu;
 constexpr unsigned RR_FULL = 0xFFFFFFFFu;

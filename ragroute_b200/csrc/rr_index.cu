@@ -31,6 +31,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <new>
 
 #include "rr_index_internal.cuh"
@@ -38,8 +39,16 @@
 
 // ------------------------------------------------------------------ kernels --
 
-// index.add: fp32 rows -> hi/lo planes (+ zero padding to d_pad) and max row norm.
+// index.add: fp32 rows -> hi/lo planes (+ zero padding to d_pad); per corpus the largest row norm
+// max|x| and the largest norm of a row's bf16 ROUNDING ERROR max|x - bf16(x)| (both feed the
+// certificate's error bound, see rr_finalize_one).  Squares are exact in fp64 and so is x - bf16(x)
+// in fp32 (Sterbenz), so both maxima are upper bounds once rounded up.
 // one warp per row
+__device__ __forceinline__ uint32_t rr_norm_bits_up(double sumsq) {
+    // sqrt in double is correctly rounded; the factor covers its half ulp and the summation error
+    return __float_as_uint(__double2float_ru(sqrt(sumsq) * (1.0 + 1e-12)));
+}
+
 __global__ void __launch_bounds__(256)
 rr_split_rows_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
@@ -47,29 +56,30 @@ rr_split_rows_kernel(const float* __restrict__ x, int64_t n, int d, int d_pad,
     const int lane = threadIdx.x & 31;
     const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    float block_max = 0.f;
+    double max_ss = 0.0, max_es = 0.0;
     for (int64_t row = warp; row < n; row += n_warps) {
         const float* xr = x + row * d;
         uint16_t* hr = hi + row * d_pad;
         uint16_t* lr = lo + row * d_pad;
-        float ss = 0.f;
+        double ss = 0.0, es = 0.0;
         for (int e = lane; e < d_pad; e += 32) {
             uint16_t h = 0, l = 0x8000u;  // joins back to +0.0f
             if (e < d) {
                 const float v = xr[e];
                 rr_split_f32(v, h, l);
-                ss = fmaf(v, v, ss);
+                const float dv = v - __uint_as_float((uint32_t)h << 16);
+                ss = fma((double)v, (double)v, ss);
+                es = fma((double)dv, (double)dv, es);
             }
             hr[e] = h;
             lr[e] = l;
         }
-        ss = rr_warp_sum(ss);
-        block_max = fmaxf(block_max, ss);
+        max_ss = fmax(max_ss, rr_warp_sum(ss));
+        max_es = fmax(max_es, rr_warp_sum(es));
     }
-    if (lane == 0 && block_max > 0.f) {
-        // upper bound of the row norm: sqrt rounded up a little
-        const float nr = sqrtf(block_max) * 1.000001f;
-        atomicMax(max_norm_bits, __float_as_uint(nr));  // positive floats order as uints
+    if (lane == 0) {  // positive floats order as uints
+        if (max_ss > 0.0) atomicMax(max_norm_bits, rr_norm_bits_up(max_ss));
+        if (max_es > 0.0) atomicMax(max_norm_bits + 1, rr_norm_bits_up(max_es));
     }
 }
 
@@ -123,7 +133,7 @@ struct rr_prep_args {
     const uint8_t* mask;
     int64_t mask_stride;
     uint16_t* qbf16;
-    float* qnorm;
+    float* qnorm;  // [2][nq_pad]: |bf16(q)|, then |q - bf16(q)| (both rounded up)
     uint8_t* active;
     uint8_t* fail_flags;
     int* fail_list;
@@ -203,23 +213,32 @@ rr_prep_queries_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
     }
     const bool act = a.mask ? (a.mask[(int64_t)b * a.mask_stride] != 0) : true;
     const float* qr = a.q + (int64_t)b * d;
-    __shared__ float part[4];
-    float ss = 0.f;
+    // |bf16(q)| and |q - bf16(q)| for the certificate, accumulated in fp64 (squares are exact there)
+    __shared__ double part[2][4];
+    double hs = 0.0, es = 0.0;
     for (int e = threadIdx.x; e < d_pad; e += blockDim.x) {
         uint16_t h = 0, l = 0;
         if (e < d && act) {
             const float v = qr[e];
             rr_split_f32(v, h, l);
-            ss = fmaf(v, v, ss);
+            const float vh = __uint_as_float((uint32_t)h << 16);
+            const float dv = v - vh;
+            hs = fma((double)vh, (double)vh, hs);
+            es = fma((double)dv, (double)dv, es);
         }
         (void)l;
         out[e] = h;
     }
-    ss = rr_warp_sum(ss);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = ss;
+    hs = rr_warp_sum(hs);
+    es = rr_warp_sum(es);
+    if ((threadIdx.x & 31) == 0) {
+        part[0][threadIdx.x >> 5] = hs;
+        part[1][threadIdx.x >> 5] = es;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        a.qnorm[b] = sqrtf(part[0] + part[1] + part[2] + part[3]) * 1.000001f;
+        a.qnorm[b] = __uint_as_float(rr_norm_bits_up(part[0][0] + part[0][1] + part[0][2] + part[0][3]));
+        a.qnorm[a.nq_pad + b] = __uint_as_float(rr_norm_bits_up(part[1][0] + part[1][1] + part[1][2] + part[1][3]));
         a.active[b] = act ? 1 : 0;
         a.fail_flags[b] = 0;
         if (act) {
@@ -384,7 +403,8 @@ struct rr_finalize_args {
     int k;
     int kprime;
     const float* q;  // [nq, d]
-    const float* qnorm;
+    const float* qnorm;  // [2][nq_pad]: |bf16(q)|, |q - bf16(q)|
+    int nq_pad;
     const uint16_t* hi;
     const uint16_t* lo;
     int d;
@@ -708,19 +728,27 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
     if (RESCORE) {
         const float bound = fmaxf(T, t_rest);
         if (bound != RR_NEG_INF) {
-            // |bf16 score - exact score| <= eps for EVERY row:
-            //   (2^-8 + 2^-18) |q||x|   both operands rounded to bf16 (rel. 2^-9 each)
-            // + d_pad * 2^-22   |q||x|   fp32 accumulation slack in the tensor core
-            const double xn = (double)__uint_as_float(*a.max_norm_bits);
-            const double qn = (double)a.qnorm[qi];
-            const double eps = (3.90625e-3 + 3.814697265625e-6 + (double)a.d_pad * 2.384185791015625e-7) *
-                                   qn * xn * 1.00001 + 1e-30;
+            // |bf16 score - exact score| <= eps for EVERY row x of the corpus.  With qh = bf16(q), xh = bf16(x):
+            //   qh.xh - q.x = qh.(xh - x) + (qh - q).x, hence by Cauchy-Schwarz
+            //   |qh.xh - q.x| <= |qh| max|xh - x| + |qh - q| max|x|
+            // with the ACTUAL rounding-error norms (measured at add / prep time, fp64, rounded up) instead of
+            // the worst case 2^-8 per operand -- sound for any data (rows sitting on bf16 midpoints simply get
+            // the full (2^-7 + 2^-16)|q||x|) and ~2.5x tighter for real embeddings.  Plus
+            //   d_pad * 2^-22 |qh||xh|   fp32 accumulation slack in the tensor core (products are exact)
+            //   2^-23 |s_k|              the k-th exact score is itself rounded once to fp32
+            const double xn = (double)__uint_as_float(a.max_norm_bits[0]);
+            const double dxn = (double)__uint_as_float(a.max_norm_bits[1]);
+            const double qhn = (double)a.qnorm[qi];
+            const double dqn = (double)a.qnorm[a.nq_pad + qi];
             const bool have_k = (kp >= a.k) && sel_r[a.k - 1] != RR_NO_ROW;
-            pass = have_k && ((double)sel_s[a.k - 1] > (double)bound + eps);
+            const double sk = have_k ? (double)sel_s[a.k - 1] : 0.0;
+            const double eps = (qhn * dxn + dqn * xn + (double)a.d_pad * 2.384185791015625e-7 * qhn * (xn + dxn)) * 1.00001 +
+                               fabs(sk) * 1.1920928955078125e-7 + 1e-30;
+            pass = have_k && (sk > (double)bound + eps);
             // L = the k-th exact score among the candidates is a lower bound of the true k-th score, and a
             // row with exact score >= L has bf16 score >= L - eps: the second pass collects every row
             // whose bf16 score is > theta = the largest float below L - eps
-            if (!pass && have_k) theta = nextafterf(__double2float_rd((double)sel_s[a.k - 1] - eps), RR_NEG_INF);
+            if (!pass && have_k) theta = nextafterf(__double2float_rd(sk - eps), RR_NEG_INF);
         }
     }
     if (pass) {
@@ -968,6 +996,7 @@ extern "C" int rr_index_create(int d, int64_t capacity_rows, int device, rr_inde
     RR_REQUIRE(capacity_rows >= 0, "rr_index_create: negative capacity");
     int rc = rr_check_device_arch(device);
     if (rc != RR_OK) return rc;
+    RR_REQUIRE(device < RR_MAX_DEVICES, "rr_index_create: device %d >= %d", device, RR_MAX_DEVICES);
     rr_device_guard g(device);
     rr_index* h = new (std::nothrow) rr_index();
     RR_REQUIRE(h != nullptr, "rr_index_create: out of host memory");
@@ -984,6 +1013,8 @@ extern "C" int rr_index_create(int d, int64_t capacity_rows, int device, rr_inde
     h->sm_count = prop.multiProcessorCount;
     e = cudaMalloc(&h->max_norm_bits, 16);
     if (e == cudaSuccess) e = cudaMemset(h->max_norm_bits, 0, 16);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->add_event, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_nfail_total, 32);
     if (e == cudaSuccess) e = cudaMemset(h->d_nfail_total, 0, 32);
     if (e != cudaSuccess) {
@@ -1008,6 +1039,8 @@ extern "C" int rr_index_destroy(rr_index_t* h) {
     cudaDeviceSynchronize();
     for (int i = 0; i < rr_index::kEvPool; ++i)
         if (h->ev_pool[i]) cudaEventDestroy(h->ev_pool[i]);
+    if (h->host_stream) cudaStreamDestroy(h->host_stream);
+    if (h->add_event) cudaEventDestroy(h->add_event);
     cudaFree(h->hi);
     cudaFree(h->lo);
     cudaFree(h->max_norm_bits);
@@ -1034,6 +1067,8 @@ extern "C" int rr_index_reserve(rr_index_t* h, int64_t capacity_rows) {
                      (long long)capacity_rows, cudaGetErrorString(e));
         return RR_ERR_OOM;
     }
+    // earlier asynchronous adds / searches (any stream) may still touch the old planes
+    RR_CUDA_CHECK(cudaDeviceSynchronize());
     if (h->n > 0) {
         const size_t used = (size_t)h->n * h->d_pad * sizeof(uint16_t);
         RR_CUDA_CHECK(cudaMemcpy(nhi, h->hi, used, cudaMemcpyDeviceToDevice));
@@ -1092,6 +1127,10 @@ extern "C" int rr_index_add_f32(rr_index_t* h, const float* x, int64_t n, int x_
         }
     }
     h->n += n;
+    if (x_on_device) {  // consumed asynchronously: rr_index_search_host (own stream) orders itself after it
+        RR_CUDA_CHECK(cudaEventRecord(h->add_event, stream));
+        h->add_event_pending = true;
+    }
     return RR_OK;
 }
 
@@ -1178,7 +1217,7 @@ extern "C" int rr_index_get_stats(rr_index_t* h, rr_index_stats* out, int reset)
         h->stats.scan_launches = 0;
         h->stats.scan_bytes_total = 0;
         h->stats.scan_flops_total = 0;
-        RR_CUDA_CHECK(cudaMemset(h->d_nfail_total + 2, 0, 16));
+        RR_CUDA_CHECK(cudaMemset(h->d_nfail_total, 0, 32));  // failure counters too
     }
     return RR_OK;
 }
@@ -1274,7 +1313,7 @@ static int rr_plan_chunk(rr_index* h, const float* q_dev, int nq, const uint8_t*
     const int nq_pad = p->nq_pad, nq_pad2 = p->nq_pad2;
     const size_t o_ctl = carve(sizeof(rr_chunk_ctl));
     const size_t o_qbf = carve((size_t)nq_pad * h->d_pad * sizeof(uint16_t));
-    const size_t o_qn = carve((size_t)nq_pad * sizeof(float));
+    const size_t o_qn = carve((size_t)nq_pad * 2 * sizeof(float));
     const size_t o_act = carve((size_t)nq_pad);
     const size_t o_ff = carve((size_t)nq_pad);
     const size_t o_fl = carve((size_t)nq_pad * sizeof(int));
@@ -1370,15 +1409,15 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
     RR_REQUIRE(fin_smem[1] <= (200u << 10), "dimension %d too large for the finalize kernel", max_dpad);
     int dev = 0;
     RR_CUDA_CHECK(cudaGetDevice(&dev));
-    static bool attr_done[64] = {};
-    if (!attr_done[dev & 63]) {
+    static std::atomic<bool> attr_done[RR_MAX_DEVICES];  // per device; a double set is harmless
+    if (!attr_done[dev].load(std::memory_order_acquire)) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_exact_scan_kernel<RR_EXACT_MAX_QSUB>,
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_finalize_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 << 10));
-        attr_done[dev & 63] = true;
+        attr_done[dev].store(true, std::memory_order_release);
     }
 
     rr_multi<rr_prep_args> pa;
@@ -1424,6 +1463,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         a.kprime = std::max(h->kprime, k);
         a.q = p.q;
         a.qnorm = p.qnorm;
+        a.nq_pad = p.nq_pad;
         a.hi = h->hi;
         a.lo = h->lo;
         a.d = h->d;
@@ -1693,6 +1733,7 @@ extern "C" int rr_federation_search(rr_index_t* const* idx, int n_sources, const
     for (int s = 0; s < n_sources; ++s) {
         idx[s]->stats.searches += 1;
         idx[s]->stats.queries += nq;
+        idx[s]->dev_dirty = true;
     }
     return RR_OK;
 }
@@ -1727,6 +1768,7 @@ extern "C" int rr_index_search_ex(rr_index_t* h, const float* q_dev, int64_t nq,
     }
     h->stats.searches += 1;
     h->stats.queries += nq;
+    h->dev_dirty = true;
     return RR_OK;
 }
 
@@ -1741,10 +1783,15 @@ extern "C" int rr_index_search(rr_index_t* h, const float* q_dev, int64_t nq, in
     return rr_index_search_ex(h, q_dev, nq, k, nullptr, 0, D_dev, I_dev, 0, stream);
 }
 
-extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t nq, int k,
-                                    float* D_host, int64_t* I_host) {
+// The reference's calling convention (numpy in, numpy out, one query at a time: data_source.py:113-120,
+// 186,199-203).  Runs on the handle's own non-blocking stream, so it does not serialise against the other
+// streams of the process; rows added asynchronously on another stream are ordered before it by the event
+// rr_index_add_f32 records.
+extern "C" int rr_index_search_host_ex(rr_index_t* h, const float* q_host, int64_t nq, int k, int flags,
+                                       float* D_host, int64_t* I_host, float* q_out_host) {
     RR_REQUIRE(h != nullptr, "rr_index_search_host: NULL handle");
     RR_REQUIRE(nq >= 0 && k > 0, "rr_index_search_host: bad nq / k");
+    RR_REQUIRE((flags & ~RR_SEARCH_NORMALIZE_L2) == 0, "rr_index_search_host: unknown flags 0x%x", flags);
     if (k > RR_MAX_K) {
         rr_set_error("rr_index_search: k=%d > RR_MAX_K=%d is not implemented", k, RR_MAX_K);
         return RR_ERR_UNSUPPORTED;
@@ -1752,27 +1799,48 @@ extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t 
     if (nq == 0) return RR_OK;
     RR_REQUIRE(q_host && D_host && I_host, "rr_index_search_host: NULL buffer");
     rr_device_guard g(h->device);
-    // device staging: [ queries | D | I | control block ]; the last three leave in ONE copy
+    const bool want_q = q_out_host != nullptr;
+    // device staging: [ queries | D | I | control block ]; the last three (all four when the normalised
+    // queries are wanted back) leave in ONE copy
     const size_t qb = rr_align_up((size_t)nq * h->d * sizeof(float), 256);
     const size_t db = rr_align_up((size_t)nq * k * sizeof(float), 256);
     const size_t ib = rr_align_up((size_t)nq * k * sizeof(int64_t), 256);
     const size_t out_b = db + ib + sizeof(rr_chunk_ctl);
+    const size_t pin_b = qb + out_b;
+    cudaStream_t stream = h->host_stream;
+    if (h->stage_bytes < qb + out_b) RR_CUDA_CHECK(cudaStreamSynchronize(stream));
     int rc = rr_grow((void**)&h->stage, &h->stage_bytes, qb + out_b);
     if (rc != RR_OK) return rc;
-    if (h->pin_bytes < out_b) {
+    if (h->pin_bytes < pin_b) {
         if (h->pin) cudaFreeHost(h->pin);
         h->pin = nullptr;
         h->pin_bytes = 0;
-        RR_CUDA_CHECK(cudaHostAlloc(&h->pin, out_b + out_b / 4, cudaHostAllocDefault));
-        h->pin_bytes = out_b + out_b / 4;
+        RR_CUDA_CHECK(cudaHostAlloc(&h->pin, pin_b + pin_b / 4, cudaHostAllocDefault));
+        h->pin_bytes = pin_b + pin_b / 4;
     }
     char* base = (char*)h->stage;
     float* q_dev = (float*)base;
     float* D_dev = (float*)(base + qb);
     int64_t* I_dev = (int64_t*)(base + qb + db);
     rr_chunk_ctl* ctl_dev = (rr_chunk_ctl*)(base + qb + db + ib);
-    cudaStream_t stream = 0;
+    // what comes back: [queries |] D | I | ctl, landing at the same offsets of the pinned mirror
+    const char* back_dev = want_q ? base : base + qb;
+    char* back_pin = (char*)h->pin + (want_q ? 0 : qb);
+    const size_t back_b = want_q ? qb + out_b : out_b;
+    const char* pin_out = (const char*)h->pin + qb;
+    if (h->add_event_pending) {
+        RR_CUDA_CHECK(cudaStreamWaitEvent(stream, h->add_event, 0));
+        h->add_event_pending = false;
+    }
+    if (h->dev_dirty) {  // an asynchronous device-API search may still use the handle's scratch block
+        RR_CUDA_CHECK(cudaDeviceSynchronize());
+        h->dev_dirty = false;
+    }
     RR_CUDA_CHECK(cudaMemcpyAsync(q_dev, q_host, (size_t)nq * h->d * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (flags & RR_SEARCH_NORMALIZE_L2) {
+        rc = rr_normalize_l2(q_dev, nq, h->d, stream);
+        if (rc != RR_OK) return rc;
+    }
     if (nq <= rr_chunk_size(h, nq)) {
         // One chunk -- the reference's call (nq = 1, data_source.py:186).  This caller waits for its result
         // anyway, so it runs the first pass, looks at the count of failed certificates that comes back with
@@ -1784,9 +1852,9 @@ extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t 
         for (int phase = RR_PHASE_FIRST; phase <= RR_PHASE_REPAIR; ++phase) {
             rc = rr_run_chunk(&plan, 1, (int)nq, k, stream, phase);
             if (rc != RR_OK) return rc;
-            RR_CUDA_CHECK(cudaMemcpyAsync(h->pin, D_dev, out_b, cudaMemcpyDeviceToHost, stream));
+            RR_CUDA_CHECK(cudaMemcpyAsync(back_pin, back_dev, back_b, cudaMemcpyDeviceToHost, stream));
             RR_CUDA_CHECK(cudaStreamSynchronize(stream));
-            const rr_chunk_ctl* ctl_host = (const rr_chunk_ctl*)((const char*)h->pin + db + ib);
+            const rr_chunk_ctl* ctl_host = (const rr_chunk_ctl*)(pin_out + db + ib);
             if (ctl_host->n_fail == 0) break;  // every certificate held: the results are final
         }
         h->stats.searches += 1;
@@ -1794,12 +1862,18 @@ extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t 
     } else {
         rc = rr_index_search(h, q_dev, nq, k, D_dev, I_dev, stream);
         if (rc != RR_OK) return rc;
-        RR_CUDA_CHECK(cudaMemcpyAsync(h->pin, D_dev, db + ib, cudaMemcpyDeviceToHost, stream));
+        RR_CUDA_CHECK(cudaMemcpyAsync(back_pin, back_dev, back_b - sizeof(rr_chunk_ctl), cudaMemcpyDeviceToHost, stream));
         RR_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
-    memcpy(D_host, h->pin, (size_t)nq * k * sizeof(float));
-    memcpy(I_host, (const char*)h->pin + db, (size_t)nq * k * sizeof(int64_t));
+    memcpy(D_host, pin_out, (size_t)nq * k * sizeof(float));
+    memcpy(I_host, pin_out + db, (size_t)nq * k * sizeof(int64_t));
+    if (want_q) memcpy(q_out_host, h->pin, (size_t)nq * h->d * sizeof(float));
     return RR_OK;
+}
+
+extern "C" int rr_index_search_host(rr_index_t* h, const float* q_host, int64_t nq, int k,
+                                    float* D_host, int64_t* I_host) {
+    return rr_index_search_host_ex(h, q_host, nq, k, 0, D_host, I_host, nullptr);
 }
 
 extern "C" int rr_index_tc_qtile(const rr_index_t* h) { return h ? rr_tc_scan_qtile(h) : RR_ERR_INVALID; }
@@ -1825,7 +1899,7 @@ extern "C" int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq,
     const int nq_pad = RR_TC_MAX_QTILE;
     const size_t o_ctl = carve(sizeof(rr_chunk_ctl));
     const size_t o_qbf = carve((size_t)nq_pad * h->d_pad * sizeof(uint16_t));
-    const size_t o_qn = carve((size_t)nq_pad * sizeof(float));
+    const size_t o_qn = carve((size_t)nq_pad * 2 * sizeof(float));
     const size_t o_act = carve((size_t)nq_pad);
     const size_t o_ff = carve((size_t)nq_pad);
     const size_t o_fl = carve((size_t)nq_pad * sizeof(int));

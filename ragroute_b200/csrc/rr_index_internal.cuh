@@ -33,7 +33,12 @@ struct rr_index {
     int64_t id_offset = 0;
     uint16_t* hi = nullptr;  // [cap, d_pad] bf16 plane (MMA operand)
     uint16_t* lo = nullptr;  // [cap, d_pad] remainder plane
-    uint32_t* max_norm_bits = nullptr;  // device: max row L2 norm (as float bits)
+    uint32_t* max_norm_bits = nullptr;  // device, float bits rounded up: [0] max row L2 norm, [1] max L2 norm of a
+                                        // row's bf16 rounding error |x - bf16(x)|
+    cudaStream_t host_stream = nullptr;  // rr_index_search_host runs here (non-blocking)
+    cudaEvent_t add_event = nullptr;     // recorded after an asynchronous rr_index_add_f32
+    bool add_event_pending = false;
+    bool dev_dirty = false;              // a device-API search was issued since the last host search
 
     // parameters
     int mode = RR_MODE_AUTO;

@@ -3,8 +3,8 @@
 // of per-shard top-k lists after the all-gather.
 //
 // One warp per query, a k-round select: every lane keeps the best live entry of
-// its strided slice, a shuffle arg-max picks the round's winner (ties: lower input
-// position), the winning lane rescans its slice.  L <= 4096 keys live in shared
+// its strided slice, a warp arg-max picks the round's winner (ties: see tie_before),
+// the winning lane rescans its slice.  L <= 4096 keys live in shared
 // memory; for the reference's shapes (L = S*k <= 128) that is 4 keys per lane.
 #include <algorithm>
 
@@ -13,18 +13,6 @@
 namespace {
 constexpr int kWarpsPerBlock = 4;
 constexpr uint32_t kDead = 0xFFFFFFFFu;  // key slot of an empty / already taken entry
-
-__device__ __forceinline__ void lane_best(const uint32_t* keys, int L, int lane, uint32_t& bk, int& bp) {
-    bk = 0;
-    bp = -1;
-    for (int i = lane; i < L; i += 32) {
-        const uint32_t kx = keys[i];
-        if (kx != kDead && (bp < 0 || kx > bk)) {  // strict: earlier position wins ties
-            bk = kx;
-            bp = i;
-        }
-    }
-}
 
 // Input = n_seg segments of [B, seg_len] lists (one segment per rank after the all-gather; one segment
 // for a plain merge); entry (seg, j) of query b has input position seg * seg_len + j.
@@ -42,6 +30,39 @@ struct MergeArgs {
     int32_t* osrc;
     int32_t* orank;
 };
+
+// Order of two entries with EQUAL keys.  Plain merge (list_len == 0): lower input position first.
+// Lists with source structure (list_len > 0, what rr_federation_search writes): lower source index, then
+// lower id, then lower position -- an order that does not depend on how the rows were sharded over the
+// ranks, so a row-sharded federation returns bit for bit what the unsharded one does even when equal
+// scores meet at the k-th place (for one segment it coincides with the position order: lists are
+// source-major and sorted by (score desc, row asc)).
+__device__ __forceinline__ int64_t entry_id(const MergeArgs& a, int64_t b, int pos) {
+    const int seg = pos / a.seg_len, j = pos - seg * a.seg_len;
+    return a.id[seg * a.seg_stride_id + b * a.seg_len + j];
+}
+__device__ __forceinline__ bool tie_before(const MergeArgs& a, int64_t b, int i, int j) {
+    if (a.list_len > 0) {
+        const int si = (i % a.seg_len) / a.list_len, sj = (j % a.seg_len) / a.list_len;
+        if (si != sj) return si < sj;
+        const int64_t ii = entry_id(a, b, i), ij = entry_id(a, b, j);
+        if (ii != ij) return ii < ij;
+    }
+    return i < j;
+}
+
+__device__ __forceinline__ void lane_best(const MergeArgs& a, int64_t b, const uint32_t* keys, int L, int lane,
+                                          uint32_t& bk, int& bp) {
+    bk = 0;
+    bp = -1;
+    for (int i = lane; i < L; i += 32) {
+        const uint32_t kx = keys[i];
+        if (kx != kDead && (bp < 0 || kx > bk || (kx == bk && tie_before(a, b, i, bp)))) {
+            bk = kx;
+            bp = i;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(const MergeArgs a) {
     extern __shared__ uint32_t keys_all[];
@@ -63,23 +84,28 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(cons
     __syncwarp();
     uint32_t bk;
     int bp;
-    lane_best(keys, L, lane, bk, bp);
+    lane_best(a, b, keys, L, lane, bk, bp);
     int n_out = k;
     for (int r = 0; r < k; ++r) {
-        // warp arg-max over (key desc, position asc): two warp reductions (redux.sync) -- the largest key,
-        // then the lowest position among the lanes holding it.  Key 0 never occurs (it is a NaN pattern,
-        // and NaNs are dead), so it stands for "lane has nothing left".
+        // warp arg-max: the largest key (one redux.sync); almost always a single lane holds it.  Key 0 never
+        // occurs (it is a NaN pattern, and NaNs are dead), so it stands for "lane has nothing left".
         const uint32_t wk = __reduce_max_sync(RR_FULL, bp >= 0 ? bk : 0u);
-        const uint32_t wpu = __reduce_min_sync(RR_FULL, (bp >= 0 && bk == wk) ? (uint32_t)bp : 0xFFFFFFFFu);
-        if (wpu == 0xFFFFFFFFu) {  // fewer than k live entries
+        unsigned holders = __ballot_sync(RR_FULL, bp >= 0 && bk == wk);
+        if (holders == 0) {  // fewer than k live entries
             n_out = r;
             break;
         }
-        const int wp = (int)wpu;
+        int wp = __shfl_sync(RR_FULL, bp, __ffs(holders) - 1);
+        holders &= holders - 1;
+        while (holders) {  // equal keys in several lanes: the tie order decides (warp-uniform)
+            const int cp = __shfl_sync(RR_FULL, bp, __ffs(holders) - 1);
+            holders &= holders - 1;
+            if (tie_before(a, b, cp, wp)) wp = cp;
+        }
         if (lane == 0) wins[r] = wp;
         if ((wp & 31) == lane) {  // owner of the winning slot retires it and rescans
             keys[wp] = kDead;
-            lane_best(keys, L, lane, bk, bp);
+            lane_best(a, b, keys, L, lane, bk, bp);
         }
         __syncwarp();
     }

@@ -35,6 +35,7 @@
 // nqt - 1 reads hit L2.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = A loader + epilogue.
 #include <algorithm>
+#include <atomic>
 
 #include "rr_index_internal.cuh"
 #include "rr_ptx.cuh"
@@ -569,11 +570,11 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     RR_REQUIRE(p.stages >= 2, "rr_gemm_scan: d_pad=%d leaves room for %d TMA stage(s) with %d CTA(s) per query tile",
                p.d_pad, p.stages, CG);
     const size_t smem = fixed + (size_t)p.stages * stage_b;
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    static std::atomic<bool> attr_done[RR_MAX_DEVICES];  // per (instantiation, device); a double set is harmless
+    if (!attr_done[h->device].load(std::memory_order_acquire)) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
-        attr_done[h->device & 63] = true;
+        attr_done[h->device].store(true, std::memory_order_release);
     }
     // every SM gets a CTA; the kernel itself splits them into query tiles x corpus slices
     cudaLaunchConfig_t cfg = {};

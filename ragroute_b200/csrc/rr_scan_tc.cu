@@ -20,6 +20,7 @@
 // (each owns the 32 TMEM lanes = 32 corpus rows of its quadrant and keeps, per
 // query, a sorted top-16 list in shared memory; see rr_topm.cuh).
 #include <algorithm>
+#include <atomic>
 
 #include "rr_index_internal.cuh"
 #include "rr_ptx.cuh"
@@ -333,11 +334,11 @@ SmemPlan plan_smem(int d_pad, int qt) {
 template <int QT>
 int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, size_t smem, bool chain,
               cudaStream_t stream) {
-    static bool attr_done[64] = {};
-    if (!attr_done[h->device & 63]) {
+    static std::atomic<bool> attr_done[RR_MAX_DEVICES];  // per (instantiation, device); a double set is harmless
+    if (!attr_done[h->device].load(std::memory_order_acquire)) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_tc_scan_kernel<QT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
-        attr_done[h->device & 63] = true;
+        attr_done[h->device].store(true, std::memory_order_release);
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);

@@ -48,6 +48,7 @@ class IndexFlatIP:
         h = _lib.c_void_p()
         _lib.check(self._lib.rr_index_create(self.d, int(reserve), self.device, _lib.ctypes.byref(h)))
         self._h = h
+        self.id_offset = 0
 
     # -- faiss surface ---------------------------------------------------------
     @property
@@ -71,8 +72,13 @@ class IndexFlatIP:
         assert x.ndim == 2 and x.shape[1] == self.d, "add: x must be [n, d]"
         _lib.check(self._lib.rr_index_add_f32(self._h, x.ctypes.data, x.shape[0], 0, None))
 
-    def search(self, x, k: int) -> Tuple[np.ndarray, np.ndarray]:
-        """index.search(x, k): numpy in, numpy out (the reference's convention)."""
+    def search(self, x, k: int, normalize: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+        """index.search(x, k): numpy in, numpy out (the reference's convention).
+
+        normalize=True folds ``faiss.normalize_L2(x)`` (data_source.py:199) into the same host round trip:
+        the queries are L2-normalised on the device before the scan and x is updated in place, exactly
+        what the reference's two calls leave behind."""
+        xin = x
         x = np.ascontiguousarray(x, dtype=np.float32)
         assert x.ndim == 2, "search: x must be 2-D"
         nq, d = x.shape
@@ -80,15 +86,27 @@ class IndexFlatIP:
         assert k > 0, "search: k must be > 0"
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        _lib.check(self._lib.rr_index_search_host(self._h, x.ctypes.data, nq, int(k), D.ctypes.data, I.ctypes.data))
+        if normalize:
+            _lib.check(self._lib.rr_index_search_host_ex(self._h, x.ctypes.data, nq, int(k), _lib.RR_SEARCH_NORMALIZE_L2,
+                                                         D.ctypes.data, I.ctypes.data, x.ctypes.data))
+            if x is not xin and isinstance(xin, np.ndarray):
+                xin[...] = x
+        else:
+            _lib.check(self._lib.rr_index_search_host(self._h, x.ctypes.data, nq, int(k), D.ctypes.data, I.ctypes.data))
         return D, I
+
+    def reconstruct_tensor(self, i0: int, n: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Rows [i0, i0 + n) as an fp32 CUDA tensor [n, d], bit-exact (asynchronous on the current stream)."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty((n, self.d), dtype=torch.float32, device="cuda")
+            assert out.is_cuda and out.dtype == torch.float32 and out.is_contiguous() and out.shape == (n, self.d)
+            _lib.check(self._lib.rr_index_reconstruct(self._h, int(i0), int(n), out.data_ptr(), _stream_ptr()))
+        return out
 
     def reconstruct_n(self, i0: int = 0, n: int = -1) -> np.ndarray:
         n = self.ntotal - i0 if n < 0 else n
-        with torch.cuda.device(self.device):
-            out = torch.empty((n, self.d), dtype=torch.float32, device="cuda")
-            _lib.check(self._lib.rr_index_reconstruct(self._h, int(i0), int(n), out.data_ptr(), _stream_ptr()))
-            return out.cpu().numpy()
+        return self.reconstruct_tensor(i0, n).cpu().numpy()
 
     def reconstruct(self, i: int) -> np.ndarray:
         return self.reconstruct_n(i, 1)[0]
@@ -142,6 +160,7 @@ class IndexFlatIP:
 
     def set_id_offset(self, offset: int) -> None:
         _lib.check(self._lib.rr_index_set_id_offset(self._h, int(offset)))
+        self.id_offset = int(offset)
 
     def reserve(self, rows: int) -> None:
         _lib.check(self._lib.rr_index_reserve(self._h, int(rows)))
@@ -165,13 +184,17 @@ class IndexFlatIP:
             n = nl.value * dp.value
             return cs[:, :n].clone(), cr[:, :n].clone(), nl.value, dp.value
 
-    def __del__(self):
+    def close(self) -> None:
+        """Free the device memory now (the handle is unusable afterwards)."""
         h, self._h = getattr(self, "_h", None), None
         if h is not None and _lib is not None:
             try:
                 self._lib.rr_index_destroy(h)
             except Exception:
                 pass
+
+    def __del__(self):
+        self.close()
 
 
 def normalize_L2(x: np.ndarray) -> None:

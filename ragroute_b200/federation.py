@@ -138,7 +138,7 @@ class Federation:
     def __init__(self, sources: Dict[str, object], k: int, router: Optional[FusedCorpusRouter] = None,
                  routing: str = "ragroute", threshold: float = DEFAULT_THRESHOLD, descending: bool = True,
                  dataset: str = "medrag", group=None, distributed: bool = False, seed: int = 0,
-                 fused: bool = True):
+                 fused: bool = True, slot_of_source: Optional[Sequence[int]] = None, d_max: int = 0):
         if routing not in ROUTING_STRATEGIES:
             raise ValueError(f"Unknown routing strategy: {routing}")  # router.py:239
         if routing == "ragroute" and router is None:
@@ -154,6 +154,10 @@ class Federation:
         self.group = group
         self.distributed = distributed
         self.fused = fused  # False: one rr_index_search_ex call per source (testing)
+        # several query encoders (FeB4RAG, config.py:44-58): which encoder's embedding each source consumes
+        # and the router's padded width (EMBEDDING_MAX_LENGTH, config.py:92-95); None = one shared embedding
+        self.slot_of_source = None if slot_of_source is None else [int(x) for x in slot_of_source]
+        self.d_max = int(d_max)
         self._packed: Optional[PackedLists] = None
         self._host_out: Dict[int, torch.Tensor] = {}  # pinned result buffers of search_host, per batch size
         self._rng = random.Random(seed)
@@ -227,14 +231,31 @@ class Federation:
         scores, ids, _, src, rank = merge_packed(packed, k, k, descending=self.descending, out=out)
         return {"scores": scores, "ids": ids, "source": src, "rank": rank, "mask": mask, "_block": out}
 
+    def search_slots(self, q_slots: Sequence[torch.Tensor]):
+        """One embedding per query ENCODER (q_slots[e] fp32 CUDA [B, d_e]; FeB4RAG-shaped federations):
+        the router sees them zero padded side by side, every source searches with its encoder's embedding."""
+        assert self.slot_of_source is not None, "this federation has a single encoder: use search(q)"
+        q_list = [q_slots[e] for e in self.slot_of_source]
+        q_router = None
+        if self.routing == "ragroute":
+            B = q_slots[0].shape[0]
+            q_router = torch.zeros((B, len(q_slots), self.d_max), dtype=torch.float32, device=q_slots[0].device)
+            for e, q in enumerate(q_slots):
+                q_router[:, e, :q.shape[1]] = q
+        mask = self.route(q_list[0] if q_router is None else q_router)
+        D_loc, I_loc = self.search_sources(q_list, mask)
+        return self.merge(D_loc, I_loc, mask)
+
     # -- host-buffer entry point (what a server process calls) --------------------------
-    def search_host(self, q_host: torch.Tensor):
-        """q_host: pinned CPU tensor [B, d].  Copies in, runs the step, copies the top-k
-        (scores, ids, source) out -- one device-to-host copy of 16 k bytes per query into a pinned
-        buffer kept per batch size -- and synchronises.  The returned arrays are views of that buffer:
-        valid until the next call with the same batch size."""
-        q = q_host.to("cuda", non_blocking=True)
-        out = self.search(q)
+    def search_host(self, q_host):
+        """q_host: pinned CPU tensor [B, d] (or one per encoder, see search_slots).  Copies in, runs the
+        step, copies the top-k (scores, ids, source) out -- one device-to-host copy of 16 k bytes per query
+        into a pinned buffer kept per batch size -- and synchronises.  The returned arrays are views of that
+        buffer: valid until the next call with the same batch size."""
+        if isinstance(q_host, (list, tuple)):
+            out = self.search_slots([q.to("cuda", non_blocking=True) for q in q_host])
+        else:
+            out = self.search(q_host.to("cuda", non_blocking=True))
         blk: MergeOut = out["_block"]
         B, k, n = blk.B, blk.k, blk.B * blk.k
         host = self._host_out.get(B)

@@ -15,6 +15,41 @@ from ragroute_b200 import synthetic as syn  # noqa: E402
 from ragroute_b200.workloads import build_medrag_federation  # noqa: E402
 
 
+def tie_case(rank, world, local):
+    """Small-integer corpora: scores are exact in bf16 and most of them are equal, documents are duplicated
+    across the two sources and across the shards -- the merge's tie order (score, source, id) must make the
+    sharded result equal the unsharded one bit for bit."""
+    import numpy as np
+    from ragroute_b200.faiss_compat import IndexFlatIP
+    from ragroute_b200.federation import Federation, shard_rows
+    rng = np.random.default_rng(7)
+    d, k = 64, 32
+    corpora = {"a": rng.integers(-2, 3, size=(5003, d)).astype(np.float32)}
+    corpora["b"] = np.concatenate([corpora["a"][1000:3000], rng.integers(-2, 3, size=(1500, d)).astype(np.float32)])
+    def build(w, r):
+        src = {}
+        for n, x in corpora.items():
+            lo, hi = shard_rows(len(x), w, r)
+            ix = IndexFlatIP(d, device=local)
+            if hi > lo:
+                ix.add(x[lo:hi])
+            ix.set_id_offset(lo)
+            src[n] = ix
+        return Federation(src, k, routing="all", distributed=w > 1)
+    sharded, whole = build(world, rank), build(1, 0)
+    bad = 0
+    for B in (3, 70, 400):
+        q = torch.from_numpy(rng.integers(-2, 3, size=(B, d)).astype(np.float32)).cuda()
+        a, b = sharded.search(q), whole.search(q)
+        torch.cuda.synchronize()
+        same = all(torch.equal(a[key], b[key]) for key in ("scores", "ids", "source"))
+        n_tied = int((a["scores"][:, :-1] == a["scores"][:, 1:]).sum().item())
+        if rank == 0:
+            print(f"world={world} B={B}: tie-heavy federation sharded == unsharded: {same} ({n_tied} adjacent ties)", flush=True)
+        bad += (not same) or n_tied == 0
+    return bad
+
+
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -45,6 +80,7 @@ def main():
         if rank == 0:
             print(f"world={world} B={B}: sharded == unsharded: {same}; ranks consistent: {ok_rank}", flush=True)
         bad += (not same) or (not ok_rank)
+    bad += tie_case(rank, world, local)
     t = torch.tensor([bad], device="cuda")
     dist.all_reduce(t)
     dist.barrier()

@@ -481,3 +481,53 @@ def test_fuzz_auto_equals_exact(faiss, seed):
     if len(sel):
         Dr, Ir = oracle.search_seq(q[sel], xb, k)
         oracle.compare_topk(De[sel], np.where(Ie[sel] >= 0, Ie[sel] - offset, -1), Dr, Ir, x=q[sel], xb=xb)
+
+
+@pytest.mark.parametrize("nq", [1, 40, 300])
+def test_certificate_is_sound_at_bf16_midpoints(faiss, nq):
+    """Worst case of the bf16 rounding error: query and the true top rows sit just below bf16
+    midpoints in every coordinate, so the tensor-core scan under-scores them by 2^-7 relative, while decoy rows
+    whose coordinates are (mostly) bf16-exact are under-scored by much less and fill every candidate list.  A
+    certificate that assumes 2^-9 per operand accepts the decoys; the bound from the measured rounding-error
+    norms must reject them and the repair path must return the exact top-k."""
+    d, k, n = 768, 32, 6000
+    u = np.float32(2.0 ** -8)
+    m = np.array([0x3F807FFF], dtype=np.uint32).view(np.float32)[0]      # 1 + 2^-8 - 2^-23: rounds DOWN to 1.0
+    p, lo = np.float32(1.0) + 2 * u, np.float32(1.0) - u                  # bf16-exact neighbours
+    rng = np.random.default_rng(5)
+    xb = (0.3 * rng.standard_normal((n, d))).astype(np.float32)          # filler: low scores
+    pattern = np.array([p] * (d // 4) + [m] * (d // 2) + [lo] * (d // 4), dtype=np.float32)
+    decoys = np.arange(0, n, 3)
+    for r in decoys:                                                     # exact 768 m (1 + 0.75 u), bf16 768 (1 + 0.25 u)
+        xb[r] = rng.permutation(pattern)
+    top = np.array([r for r in range(1, n, 149)][:40])                   # exact 768 m^2, bf16 768.0: below every decoy
+    xb[top] = m
+    q = np.full((nq, d), m, dtype=np.float32)
+    ix = _index(faiss, xb, "auto")
+    D, I = ix.search(q, k)
+    st = ix.stats()
+    De, Ie = _index(faiss, xb, "exact").search(q, k)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De), f"auto differs from exact at bf16 midpoints: {st}"
+    assert I[0].tolist() == sorted(top.tolist())[:k], "the rows at the midpoints are the true top-k"
+    assert st["exact_rescans"] == nq, f"every certificate must fail here: {st}"
+
+
+def test_search_with_normalize_is_one_call_and_in_place(faiss):
+    """retrieve_docs_wikipedia (data_source.py:199-203): normalize_L2 + search as one host round trip."""
+    rng = np.random.default_rng(8)
+    xb = rng.standard_normal((5000, 768), dtype=np.float32)
+    xb /= np.linalg.norm(xb, axis=1, keepdims=True)
+    q = rng.standard_normal((3, 768), dtype=np.float32) * 7
+    ix = _index(faiss, xb, "auto")
+    q1, q2 = q.copy(), q.copy()
+    faiss.normalize_L2(q1)
+    D1, I1 = ix.search(q1, 10)
+    D2, I2 = ix.search(q2, 10, normalize=True)
+    assert np.array_equal(I1, I2) and np.array_equal(D1, D2)
+    assert np.array_equal(q1, q2), "normalize=True must leave the normalised queries in the caller's array"
+    # a device-API search followed by a host search on the same handle (different streams) stays ordered
+    qt = torch.from_numpy(q1).cuda()
+    Dt, It = ix.search_tensor(qt, 10)
+    D3, I3 = ix.search(q1, 10)
+    torch.cuda.synchronize()
+    assert np.array_equal(It.cpu().numpy(), I3) and np.array_equal(Dt.cpu().numpy(), D3)

@@ -128,11 +128,48 @@ def test_merge_segments_in_place_vs_oracle(cuda_required, B, W, S, k, descending
     s, i, pos, src, rank = merge_packed(pl, k, k, descending)
     cat_s = np.concatenate(list(scores), axis=1)
     cat_i = np.concatenate(list(ids), axis=1)
-    rs, ri, rp = rerank_ref.merge_topk(cat_s, cat_i, k, descending)
+    rs, ri, rp = rerank_ref.merge_topk(cat_s, cat_i, k, descending, seg_len=L, list_len=k)
     assert np.array_equal(s.cpu().numpy(), rs) and np.array_equal(i.cpu().numpy(), ri)
     assert np.array_equal(pos.cpu().numpy(), rp)
     r_ref, s_ref = decode_pos(torch.from_numpy(rp), S, k)
     assert np.array_equal(rank.cpu().numpy(), r_ref.numpy()) and np.array_equal(src.cpu().numpy(), s_ref.numpy())
+
+
+@pytest.mark.parametrize("W", [2, 3, 8])
+def test_sharded_merge_equals_unsharded_with_cross_rank_ties(cuda_required, W):
+    """equal scores from different sources / ranks must come back in the same order whether
+    the corpus is one shard or W (duplicated documents across corpora produce exactly such ties).  Per
+    (query, source) a pool of scored rows with many equal scores; the unsharded lists are each source's
+    top-k by (score desc, row asc), the sharded ones each (rank, source)'s top-k of its contiguous rows."""
+    from ragroute_b200.federation import PackedLists, merge_packed
+    rng = np.random.default_rng(W)
+    B, S, k, n = 40, 3, 8, 60
+    per = -(-n // W)
+    whole = PackedLists(B, S * k, "cuda", n_blocks=1)
+    shard = PackedLists(B, S * k, "cuda", n_blocks=W)
+    fmax = np.finfo(np.float32).max
+    ws, wi = np.full((B, S * k), -fmax, np.float32), np.full((B, S * k), -1, np.int64)
+    ss, si = np.full((W, B, S * k), -fmax, np.float32), np.full((W, B, S * k), -1, np.int64)
+    for b in range(B):
+        for s in range(S):
+            sc = rng.integers(0, 6, size=n).astype(np.float32)             # 6 distinct scores over 60 rows
+            order = np.lexsort((np.arange(n), -sc))
+            top = order[:k]
+            ws[b, s * k:(s + 1) * k], wi[b, s * k:(s + 1) * k] = sc[top], top
+            for r in range(W):
+                rows = np.arange(r * per, min(n, (r + 1) * per))
+                o = rows[np.lexsort((rows, -sc[rows]))][:k]
+                ss[r, b, s * k:s * k + len(o)], si[r, b, s * k:s * k + len(o)] = sc[o], o
+    whole.scores().copy_(torch.from_numpy(ws)); whole.ids().copy_(torch.from_numpy(wi))
+    for r in range(W):
+        shard.scores(r).copy_(torch.from_numpy(ss[r])); shard.ids(r).copy_(torch.from_numpy(si[r]))
+    a = merge_packed(whole, k, k)
+    c = merge_packed(shard, k, k)
+    torch.cuda.synchronize()
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1]) and torch.equal(a[3], c[3]), \
+        "sharded merge must equal the unsharded one bit for bit, ties included"
+    rs, ri, _ = rerank_ref.merge_topk(ws, wi, k, True, seg_len=S * k, list_len=k)
+    assert np.array_equal(a[0].cpu().numpy(), rs) and np.array_equal(a[1].cpu().numpy(), ri)
 
 
 def test_merge_segments_rejects_bad_arguments(cuda_required):

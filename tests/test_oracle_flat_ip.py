@@ -59,6 +59,22 @@ def test_blas_branch_and_dispatch_agree_with_seq():
     assert np.array_equal(Ir, Is) and np.array_equal(Dr, Ds)
 
 
+def test_blas_branch_c_heap_pass_equals_its_numpy_restatement():
+    """The C add_results heap pass (what bench.py's CPU legs time) against the vectorised numpy restatement
+    of the same rule, over several corpus blocks, with ties and with fewer rows than k."""
+    rng = np.random.default_rng(6)
+    xb = rng.integers(-3, 4, size=(2600, 32)).astype(np.float32)      # many equal scores, 3 corpus blocks
+    q = rng.integers(-2, 3, size=(33, 32)).astype(np.float32)
+    Dc, Ic = o.search_blas(q, xb, 10)
+    Dn, In = o.search_blas(q, xb, 10, numpy_heap=True)
+    assert np.array_equal(Dc, Dn)                                      # same scores; which of several rows
+    o.compare_topk(Dc, Ic, Dn, In, x=q, xb=xb)                         # TIED at the k-th score stays is heap-shaped
+    Ds, Is = o.search_seq(q, xb, 10)                                   # the sequential branch feeds the same heap
+    assert np.array_equal(Dc, Ds) and np.array_equal(Ic, Is)           # in the same row order: identical
+    D5, I5 = o.search_blas(q[:21], xb[:5], 8)
+    assert (I5[:, 5:] == -1).all() and (D5[:, 5:] == -FLT_MAX).all() and np.all(np.diff(D5[:, :5], axis=1) <= 0)
+
+
 def test_strict_greater_keeps_earlier_row_on_entry_tie():
     xb = np.ones((40, 4), dtype=np.float32)    # all scores equal
     q = np.ones((1, 4), dtype=np.float32)
