@@ -162,6 +162,13 @@ int rr_index_debug_tc_scan(rr_index_t* h, const float* q_dev, int nq, float* can
                            uint32_t* cand_r_dev, int64_t capacity, int* n_lists, int* depth,
                            void* stream);
 
+/* faiss.read_index(path) (data_source.py:71) for a flat inner-product index file (fourcc "IxFI" / "IxFl",
+ * metric 0): creates the index on `device` and streams the fp32 rows disk -> pinned host -> device with
+ * double buffering (the file never has to fit in host memory).  Any other index type: RR_ERR_INVALID.
+ * rr_index_write is the inverse (faiss.write_index layout, "IxFI"). */
+int rr_index_read(const char* path, int device, rr_index_t** out);
+int rr_index_write(rr_index_t* h, const char* path);
+
 /* faiss.normalize_L2(x) (data_source.py:199), in place on device rows [n, d] */
 int rr_normalize_l2(float* x_dev, int64_t n, int d, void* stream);
 

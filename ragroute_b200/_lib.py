@@ -58,6 +58,8 @@ _SIGNATURES = {
     "rr_index_search_host_ex": (c_int, [c_void_p, _P, c_int64, c_int, c_int, _P, _P, _P]),
     "rr_federation_search": (c_int, [POINTER(c_void_p), c_int, POINTER(c_void_p), c_int64, c_int, _P, c_int64, _P, _P,
                                      c_int64, _P]),
+    "rr_index_read": (c_int, [c_char_p, c_int, POINTER(c_void_p)]),
+    "rr_index_write": (c_int, [c_void_p, c_char_p]),
     "rr_index_get_stats": (c_int, [c_void_p, POINTER(IndexStats), c_int]),
     "rr_index_tc_qtile": (c_int, [c_void_p]),
     "rr_index_debug_tc_scan": (c_int, [c_void_p, _P, c_int, _P, _P, c_int64, POINTER(c_int), POINTER(c_int), _P]),

@@ -120,12 +120,13 @@ class MicroBatcher:
 
 
 # -- batch functions for the three call sites ---------------------------------------------------
-def search_rows(index, embeddings: Sequence[np.ndarray], k: int):
+def search_rows(index, embeddings: Sequence[np.ndarray], k: int, normalize: bool = False):
     """batch_fn for a data source: embeddings as the serve loop builds them
     (``np.array(..., float32).reshape(1, -1)``, data_source.py:113-114) -> per request
-    ``(D[1, k], I[1, k])`` exactly as ``index.search(embedding, k)`` returns them."""
+    ``(D[1, k], I[1, k])`` exactly as ``index.search(embedding, k)`` returns them.
+    normalize: ``faiss.normalize_L2`` first, in the same call (retrieve_docs_wikipedia, data_source.py:199)."""
     x = np.concatenate([np.asarray(e, dtype=np.float32).reshape(1, -1) for e in embeddings], axis=0)
-    D, I = index.search(x, k)
+    D, I = index.search(x, k, normalize=True) if normalize else index.search(x, k)
     return [(D[i:i + 1], I[i:i + 1]) for i in range(len(embeddings))]
 
 

@@ -13,7 +13,7 @@ All arithmetic runs in libragroute_b200.so on the GPU; there is no CPU path.
 """
 from __future__ import annotations
 
-import struct
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -209,38 +209,24 @@ def normalize_L2(x: np.ndarray) -> None:
 
 
 # ---------------------------------------------------------------------------
-# faiss.read_index / write_index for flat indexes (upstream faiss 1.7.4 layout,
-# faiss/impl/index_write.cpp: fourcc "IxFI" | "IxF2" | "IxFl", header
-# d:int32 ntotal:int64 dummy:int64 dummy:int64 is_trained:uint8 metric:int32,
-# then uint64 count-of-floats and the raw fp32 rows).
+# faiss.read_index / write_index for flat indexes (upstream faiss 1.7.4 layout, see csrc/rr_io.cu:
+# fourcc "IxFI" | "IxFl", header d:int32 ntotal:int64 dummy:int64 dummy:int64 is_trained:uint8
+# metric:int32, then uint64 count-of-floats and the raw fp32 rows).  Both run natively: the rows stream
+# disk <-> pinned host <-> device with double buffering.
 # ---------------------------------------------------------------------------
-_HDR = struct.Struct("<4siqqqBi")
-
-
 def write_index(index: IndexFlatIP, path: str) -> None:
-    rows = index.reconstruct_n(0, index.ntotal)
-    with open(path, "wb") as f:
-        f.write(_HDR.pack(b"IxFI", index.d, index.ntotal, 1 << 20, 1 << 20, 1, METRIC_INNER_PRODUCT))
-        f.write(struct.pack("<Q", rows.size))
-        f.write(rows.tobytes())
+    _lib.check(index._lib.rr_index_write(index._h, os.fsencode(path)))
 
 
-def read_index(path: str, device: Optional[int] = None, chunk_rows: int = 1 << 18) -> IndexFlatIP:
-    """faiss.read_index(path) for a flat inner-product index, streamed to the GPU in
-    chunks (the fp32 file never has to fit in host memory at once)."""
-    with open(path, "rb") as f:
-        fourcc, d, ntotal, _, _, _, metric = _HDR.unpack(f.read(_HDR.size))
-        if fourcc not in (b"IxFI", b"IxFl") or metric != METRIC_INNER_PRODUCT:
-            raise _lib.RRError(f"{path}: only flat inner-product indexes are supported "
-                               f"(fourcc={fourcc!r}, metric={metric}); data_source.py uses IndexFlatIP")
-        (count,) = struct.unpack("<Q", f.read(8))
-        if count != ntotal * d:
-            raise _lib.RRError(f"{path}: corrupt flat index ({count} floats for {ntotal} x {d})")
-        index = IndexFlatIP(d, device=device, reserve=ntotal)
-        left = ntotal
-        while left > 0:
-            n = min(left, chunk_rows)
-            buf = np.frombuffer(f.read(n * d * 4), dtype=np.float32).reshape(n, d)
-            index.add(buf)
-            left -= n
+def read_index(path: str, device: Optional[int] = None) -> IndexFlatIP:
+    """faiss.read_index(path) (data_source.py:71) for a flat inner-product index file; anything else
+    raises (the reference's data sources are IndexFlatIP, north_star)."""
+    _lib.require_cuda()
+    lib = _lib.load()
+    dev = torch.cuda.current_device() if device is None else int(device)
+    h = _lib.c_void_p()
+    _lib.check(lib.rr_index_read(os.fsencode(path), dev, _lib.ctypes.byref(h)))
+    index = IndexFlatIP.__new__(IndexFlatIP)
+    index._lib, index._h, index.device, index.id_offset = lib, h, dev, 0
+    index.d = int(lib.rr_index_dim(h))
     return index

@@ -48,6 +48,28 @@ def unpack_message(frames: List[bytes]) -> Tuple[dict, Dict[str, np.ndarray]]:
     return h, out
 
 
+def decode_request(frames: List[bytes]) -> Tuple[dict, "np.ndarray | None"]:
+    """What a data source receives (data_source.py:102,113-114): either the frames of ``pack_message`` with one
+    embedding named "embedding", or the reference's single JSON frame with ``"embedding": [floats]`` (also the
+    "fetch" message of the second phase, which carries no embedding).  -> (message dict, fp32 embedding or None)."""
+    if frames and frames[0] == MAGIC:
+        header, embs = unpack_message(frames)
+        return header, embs.get("embedding")
+    msg = json.loads(frames[0].decode("utf-8"))
+    emb = msg.get("embedding")
+    return msg, (np.asarray(emb, dtype=np.float32) if emb is not None else None)
+
+
+def decode_routing(frames: List[bytes]) -> Tuple[dict, Dict[str, np.ndarray]]:
+    """What the server receives from the router (http_server.py:174-179): ``pack_message`` frames with one
+    embedding per encoder, or the reference's JSON with ``"embeddings": {encoder: [floats]}``."""
+    if frames and frames[0] == MAGIC:
+        return unpack_message(frames)
+    msg = json.loads(frames[0].decode("utf-8"))
+    embs = {m: np.asarray(e, dtype=np.float32) for m, e in msg.pop("embeddings", {}).items()}
+    return msg, embs
+
+
 def pack_results(query_id, client_id, name: str, ids: np.ndarray, scores: np.ndarray, duration: float) -> List[bytes]:
     """A data source's reply without document text (ids + scores only): the server fetches the text of the
     k documents that survive the global merge instead of receiving S*k documents of which (S-1)/S are

@@ -215,6 +215,60 @@ def test_reconstruct_is_bit_exact_and_index_file_roundtrip(faiss):
         assert np.array_equal(a[1], b[1]) and np.array_equal(a[0], b[0])
 
 
+def _faiss_flat_file(path, xb, fourcc=b"IxFI", metric=0):
+    """An index file laid out as upstream faiss 1.7.4 writes IndexFlat (index_write.cpp: fourcc, write_index_header,
+    then the vector of floats), produced here byte by byte -- independent of the library's own writer."""
+    import struct
+    n, d = xb.shape
+    with open(path, "wb") as f:
+        f.write(fourcc)
+        f.write(struct.pack("<i", d)); f.write(struct.pack("<q", n))
+        f.write(struct.pack("<q", 1 << 20)); f.write(struct.pack("<q", 1 << 20))
+        f.write(struct.pack("<B", 1)); f.write(struct.pack("<i", metric))
+        f.write(struct.pack("<Q", n * d))
+        f.write(np.ascontiguousarray(xb, dtype="<f4").tobytes())
+
+
+def test_read_index_streams_a_faiss_laid_out_file(faiss, tmp_path):
+    """faiss.read_index (data_source.py:71) on a hand-laid-out IxFI file larger than one streaming chunk (64 MB:
+    the double-buffered disk -> pinned -> device path really alternates buffers), bit-exact rows, same search
+    results as index.add of the same rows; the writer's output is byte-identical to the hand-laid-out file;
+    non-flat / L2 / truncated files are rejected loudly."""
+    from ragroute_b200._lib import RRError
+    rng = np.random.default_rng(12)
+    n, d = 70_001, 300                                   # 84 MB of rows: two chunks, the second partial
+    xb = rng.standard_normal((n, d), dtype=np.float32)
+    path = str(tmp_path / "faiss.index")
+    _faiss_flat_file(path, xb)
+    ix = faiss.read_index(path)
+    assert ix.ntotal == n and ix.d == d
+    for r0 in (0, 55_923, n - 7):                        # around the chunk boundary (55 924 rows per chunk) and the end
+        back = ix.reconstruct_n(r0, 7)
+        assert np.array_equal(back.view(np.uint32), xb[r0:r0 + 7].view(np.uint32))
+    q = rng.standard_normal((3, d), dtype=np.float32)
+    D, I = ix.search(q, 10)
+    D2, I2 = _index(faiss, xb).search(q, 10)
+    assert np.array_equal(I, I2) and np.array_equal(D, D2)
+    out = str(tmp_path / "written.index")
+    faiss.write_index(ix, out)
+    assert open(out, "rb").read() == open(path, "rb").read(), "write_index must reproduce the faiss layout byte for byte"
+    bad = str(tmp_path / "bad.index")
+    _faiss_flat_file(bad, xb[:10], fourcc=b"IxF2", metric=1)          # IndexFlatL2
+    with pytest.raises(RRError):
+        faiss.read_index(bad)
+    _faiss_flat_file(bad, xb[:10], fourcc=b"IwFl")                     # IVF: not a flat index
+    with pytest.raises(RRError):
+        faiss.read_index(bad)
+    with open(path, "rb") as f:
+        head = f.read(100_000)
+    with open(bad, "wb") as f:
+        f.write(head)                                                  # truncated rows
+    with pytest.raises(RRError):
+        faiss.read_index(bad)
+    with pytest.raises(RRError):
+        faiss.read_index(str(tmp_path / "missing.index"))
+
+
 def test_normalize_l2_matches_oracle(faiss):
     rng = np.random.default_rng(2)
     x = rng.standard_normal((3, 768), dtype=np.float32)
