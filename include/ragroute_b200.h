@@ -86,7 +86,8 @@ int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
  * flops they cover), "scan_path" (testing: 0 = automatic dispatch, 1 = swap-AB scan in
  * passes of <= 64 queries, 2 = queries-in-TMEM scan with one CTA per 128-query tile,
  * 3 = the same on CTA pairs), "gemm_tmem_all" (testing: 0 = keep the two-accumulator layout of the
- * queries-in-TMEM scan even for <= 128 queries) */
+ * queries-in-TMEM scan even for <= 128 queries), "gemm_depth" (testing: entries per candidate list of the
+ * queries-in-TMEM scan, 8 or 32; 0 = automatic: 8 for shards of <= 16 k rows per list) */
 int rr_index_set_param(rr_index_t* h, const char* name, double value);
 
 /* index.search(x, k) (data_source.py:158,186,203) on device buffers:

@@ -18,6 +18,12 @@ static std::atomic<long long> g_launches{0};
 void rr_count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 extern "C" int64_t rr_kernel_launches(void) { return (int64_t)g_launches.load(std::memory_order_relaxed); }
 
+#include <stdlib.h>
+bool rr_pdl_enabled() {
+    static const bool on = getenv("RR_NO_PDL") == nullptr;
+    return on;
+}
+
 extern "C" const char* rr_last_error(void) { return g_last_error; }
 extern "C" int rr_abi_version(void) { return RR_ABI_VERSION; }
 

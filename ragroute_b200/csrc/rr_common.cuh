@@ -44,6 +44,26 @@ struct rr_device_guard {
 };
 
 int rr_check_device_arch(int device);  // RR_OK iff compute capability 10.x
+bool rr_pdl_enabled();                  // false when RR_NO_PDL is set (measurement knob)
+
+#ifdef __CUDACC__
+// kernel<<<grid, block, smem, stream>>>(args...) with the programmatic-stream-serialization attribute
+template <class... KArgs, class... Args>
+static inline cudaError_t rr_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                        Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rr_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 void rr_count_launch(int n);            // process-wide count of this library's kernel launches
 
 constexpr int RR_MAX_DEVICES = 64;  // per-device one-time setup flags
@@ -70,6 +90,19 @@ __host__ __device__ __forceinline__ void rr_split_f32(float x, uint16_t& hi, uin
 }
 
 #ifdef __CUDACC__
+// ---- programmatic dependent launch (PDL) for the whole step -------------------------------------------
+// Every kernel of a step is launched with cudaLaunchAttributeProgrammaticStreamSerialization and begins with
+// rr_pdl_enter(): "launch_dependents" lets the NEXT kernel of the stream be scheduled onto the SMs while this
+// one still runs (its blocks then sit at their own wait), "wait" blocks until the PREVIOUS kernel has completed
+// and its writes are visible.  Because every kernel executes the wait before it touches global memory and
+// before it can exit, completion order stays stream order (transitively), so the step computes exactly what
+// plain stream serialisation computes -- only the launch / drain gaps between its ~12 small kernels overlap.
+// (The wait is a no-op when the kernel was launched without the attribute.)
+__device__ __forceinline__ void rr_pdl_enter() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // two elements packed per 32-bit word in each plane -> two fp32 values
 __device__ __forceinline__ float2 rr_join_f32x2(uint32_t hi_w, uint32_t lo_w) {
     uint32_t b0 = __byte_perm(lo_w, hi_w, 0x5410) - 0x8000u;

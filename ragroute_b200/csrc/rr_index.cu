@@ -99,6 +99,7 @@ rr_join_rows_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict_
 
 __global__ void __launch_bounds__(128)
 rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
+    rr_pdl_enter();
     // faiss fvec_renorm_L2: x /= sqrt(sum x^2) when the norm is positive
     const int64_t row = blockIdx.x;
     if (row >= n) return;
@@ -156,6 +157,7 @@ static_assert(RR_GEMM_QCHUNK % 1024 == 0 && kCompactPer >= 1 && kCompactPer <= 8
 
 __global__ void __launch_bounds__(1024)
 rr_begin_chunk_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
+    rr_pdl_enter();
     const rr_prep_args& a = m.s[blockIdx.x];
     __shared__ int warp_cnt[32];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
@@ -199,6 +201,7 @@ rr_begin_chunk_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
 // activity flags.  grid = (max nq_pad, sources).
 __global__ void __launch_bounds__(128)
 rr_prep_queries_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
+    rr_pdl_enter();
     const rr_prep_args& a = m.s[blockIdx.y];
     const int b = blockIdx.x;
     if (b >= a.nq_pad) return;
@@ -251,6 +254,91 @@ rr_prep_queries_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
     }
 }
 
+// begin + prep in ONE launch for chunks of <= RR_FUSED_PREP_MAX padded queries (every small-batch step: the two
+// launches cost more than their work).  One block of 1024 threads per source: zero the control block, compact the
+// routed queries (large-batch path), then one WARP per query converts it (same arithmetic as the kernel above).
+constexpr int RR_FUSED_PREP_MAX = 256;
+
+__global__ void __launch_bounds__(1024)
+rr_begin_prep_fused_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
+    rr_pdl_enter();
+    const rr_prep_args& a = m.s[blockIdx.x];
+    __shared__ int warp_cnt[32];
+    __shared__ int s_cpos[RR_FUSED_PREP_MAX];
+    __shared__ int s_any;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nq = a.nq, nq_pad = a.nq_pad, d = a.d, d_pad = a.d_pad;
+    if (nq_pad <= 0) return;
+    const uint8_t* __restrict__ mask = a.mask;
+    // routed? -- thread b < nq_pad looks at query b
+    const bool act_b = (tid < nq) && (mask ? (mask[(int64_t)tid * a.mask_stride] != 0) : true);
+    int n_active = 0;
+    if (a.compact) {
+        const unsigned bal = __ballot_sync(RR_FULL, act_b);
+        if (lane == 0) warp_cnt[w] = __popc(bal);
+        __syncthreads();
+        int before = __popc(bal & ((1u << lane) - 1u));
+        for (int i = 0; i < 32; ++i) {
+            const int c = warp_cnt[i];
+            if (i < w) before += c;
+            n_active += c;
+        }
+        if (tid < nq) {
+            const int cp = act_b ? before : n_active + (tid - before);
+            a.cpos[tid] = cp;
+            s_cpos[tid] = cp;
+        }
+    }
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    for (int b = w; b < nq_pad; b += 32) {
+        uint16_t* out = a.qbf16 + (int64_t)((a.compact && b < nq) ? s_cpos[b] : b) * d_pad;
+        if (b >= nq) {
+            for (int e = lane; e < d_pad; e += 32) out[e] = 0;
+            if (lane == 0) a.active[b] = 0;
+            continue;
+        }
+        const bool act = mask ? (mask[(int64_t)b * a.mask_stride] != 0) : true;
+        const float* qr = a.q + (int64_t)b * d;
+        double hs = 0.0, es = 0.0;
+        for (int e = lane; e < d_pad; e += 32) {
+            uint16_t h = 0, l = 0;
+            if (e < d && act) {
+                const float v = qr[e];
+                rr_split_f32(v, h, l);
+                const float vh = __uint_as_float((uint32_t)h << 16);
+                const float dv = v - vh;
+                hs = fma((double)vh, (double)vh, hs);
+                es = fma((double)dv, (double)dv, es);
+            }
+            (void)l;
+            out[e] = h;
+        }
+        hs = rr_warp_sum(hs);
+        es = rr_warp_sum(es);
+        if (lane == 0) {
+            a.qnorm[b] = __uint_as_float(rr_norm_bits_up(hs));
+            a.qnorm[nq_pad + b] = __uint_as_float(rr_norm_bits_up(es));
+            a.active[b] = act ? 1 : 0;
+            a.fail_flags[b] = a.exact_all && act ? 1 : 0;
+            if (act) s_any = 1;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {  // the whole control block, written once (no other block touches it in this launch)
+        rr_chunk_ctl c = {};
+        c.any_active = s_any;
+        c.n_active = n_active;
+        if (a.exact_all) {  // exact-only plans: every routed query goes to the exact scan, in query order
+            int nf = 0;
+            for (int b = 0; b < nq; ++b)
+                if (mask ? (mask[(int64_t)b * a.mask_stride] != 0) : true) a.fail_list[nf++] = b;
+            c.n_fail = nf;
+        }
+        *a.ctl = c;
+    }
+}
+
 // Exact scan over the queries in fail_list[blockIdx.y*qsub ...): fp32 rows rebuilt from
 // the planes, products and sums in fp64 (each product of two fp32 is exact in
 // fp64), score rounded once to fp32.  One warp per row; per-warp lists of depth
@@ -274,6 +362,7 @@ struct rr_exact_args {
 template <int QSUB>
 __global__ void __launch_bounds__(RR_EXACT_WARPS * 32)
 rr_exact_scan_kernel(const __grid_constant__ rr_multi<rr_exact_args> m) {
+    rr_pdl_enter();
     const rr_exact_args& a = m.s[blockIdx.z];
     if (a.n_rows <= 0) return;
     const uint16_t* __restrict__ hi = a.hi;
@@ -432,6 +521,8 @@ struct rr_finalize_args {
 
 constexpr int RR_FIN_THREADS = 512;
 constexpr int RR_FIN_MAXSEL = 256;
+constexpr int RR_FIN_BINS_LOG2 = 11;
+constexpr int RR_FIN_BINS = 1 << RR_FIN_BINS_LOG2;  // histogram bins of the candidate select
 
 // dynamic shared memory of a finalize block: the query (RESCORE) + the staged candidate lists
 static size_t rr_finalize_smem(bool rescore, int d_pad, int64_t stage_cap) {
@@ -466,9 +557,11 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
         }
     }
 
-    __shared__ uint32_t hist[256];
-    __shared__ unsigned long long s_prefix, s_mask;
-    __shared__ int s_remaining, s_cnt_gt, s_cnt_eq, s_nvalid;
+    __shared__ uint32_t hist[RR_FIN_BINS];
+    __shared__ unsigned long long s_kmin[RR_FIN_THREADS / 32], s_kmax[RR_FIN_THREADS / 32];
+    __shared__ unsigned long long s_lo, s_hi;
+    __shared__ int s_bstar, s_cgt, s_ceq, s_cnt_gt, s_cnt_eq, s_nvalid;
+    __shared__ uint32_t s_scan[RR_FIN_THREADS / 32];
     __shared__ float s_red[RR_FIN_THREADS / 32];
     __shared__ float sel_s[RR_FIN_MAXSEL];
     __shared__ uint32_t sel_r[RR_FIN_MAXSEL];
@@ -482,16 +575,19 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
     const uint32_t* gr = a.cand_r + (int64_t)crow * a.cand_stride;
     const int n_lists = (RESCORE && a.lists_from_ctl) ? a.ctl->n_lists : a.n_lists;
     const int n_cand = n_lists * a.depth;
-    // the select below makes 5-9 passes over the lists: from shared memory when they fit the block's
+    // the select below makes a few passes over the lists: from shared memory when they fit the block's
     // allotment (sized by the host for the batch: everything for small batches, 2048 entries -- and more
     // blocks per SM -- for large ones, whose lists are few), else in place
     const bool staged = n_cand <= a.stage_cap;
     const float* cs = staged ? cs_sm : gs;
     const uint32_t* cr = staged ? cr_sm : gr;
+    // ranking key of a candidate: larger = better.  RESCORE: the bf16 score; else (score, lower row first)
+    auto key_of = [&](float sc, uint32_t r) -> unsigned long long {
+        const unsigned long long k32 = rr_float_key(sc);
+        return RESCORE ? k32 : ((k32 << 32) | (unsigned long long)(~r));
+    };
 
     if (tid == 0) {
-        s_prefix = 0ull;
-        s_mask = 0ull;
         s_cnt_gt = 0;
         s_cnt_eq = 0;
         s_nvalid = 0;
@@ -500,10 +596,11 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
         const float* qr = a.q + (int64_t)qi * a.d;
         for (int e = tid; e < a.d_pad; e += blockDim.x) q_sm[e] = (e < a.d) ? qr[e] : 0.f;
     }
-    // stage the lists; count the occupied slots and take T = largest tail of a full list (every row a
-    // list dropped scores <= its tail)
+    // stage the lists; count the occupied slots, take T = largest tail of a full list (every row a
+    // list dropped scores <= its tail) and the range of the keys
     float T = RR_NEG_INF;
     int nv = 0;
+    unsigned long long kmin = ~0ull, kmax = 0ull;
     {
         constexpr int U = 4;
         const int depth_m1 = a.depth - 1;
@@ -527,116 +624,140 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
                     if (vr[u] != RR_NO_ROW) {
                         ++nv;
                         if ((i & depth_m1) == depth_m1) T = fmaxf(T, vs[u]);  // list depths are powers of two
+                        const unsigned long long key = key_of(vs[u], vr[u]);
+                        kmin = min(kmin, key);
+                        kmax = max(kmax, key);
                     }
                 }
             }
         }
     }
     T = rr_warp_max(T);
-    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(RR_FULL, nv, o);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nv += __shfl_xor_sync(RR_FULL, nv, o);
+        kmin = min(kmin, __shfl_xor_sync(RR_FULL, kmin, o));
+        kmax = max(kmax, __shfl_xor_sync(RR_FULL, kmax, o));
+    }
     __syncthreads();  // s_nvalid is zero, the staged lists are visible
     if (lane == 0) {
         s_red[w] = T;
+        s_kmin[w] = kmin;
+        s_kmax[w] = kmax;
         atomicAdd(&s_nvalid, nv);
     }
     __syncthreads();
     T = s_red[0];
-    for (int i = 1; i < (n_threads >> 5); ++i) T = fmaxf(T, s_red[i]);
+    kmin = s_kmin[0];
+    kmax = s_kmax[0];
+    for (int i = 1; i < (n_threads >> 5); ++i) {
+        T = fmaxf(T, s_red[i]);
+        kmin = min(kmin, s_kmin[i]);
+        kmax = max(kmax, s_kmax[i]);
+    }
     const int n_valid = s_nvalid;
     const int want = RESCORE ? min(a.kprime, RR_FIN_MAXSEL) : a.k;
-    const int kp = min(want, n_valid);
-    __syncthreads();
-    if (tid == 0) s_remaining = kp;
-    __syncthreads();
+    int kp = min(want, n_valid);
 
-    // radix select of the kp-th largest key (8 bits per pass, MSB first)
-    constexpr int NPASS = RESCORE ? 4 : 8;
+    // Select a SUPERSET of the kp best keys, at most RR_FIN_MAXSEL of them, by linear binning of the key
+    // range: one histogram pass over [lo, hi] in up to RR_FIN_BINS bins, a suffix scan finds the bin b* in
+    // which the kp-th best falls; everything above b* is taken and, if it fits, all of b* too (rescoring /
+    // sorting a few extra candidates costs less than narrowing down to exactly kp).  Only when b* is too
+    // crowded is its range binned again (long runs of near-equal scores); a single key value that still
+    // does not fit (exact ties) is cut by position.  One pass in the common case -- the 4 (8) passes of an
+    // 8-bit radix select with their 12 (24) block barriers were a third of this kernel.
     float t_rest = RR_NEG_INF;
     if (kp > 0) {
-        for (int pass = 0; pass < NPASS; ++pass) {
-            const int shift = (NPASS - 1 - pass) * 8;
-            if (tid < 256) hist[tid] = 0;
+        unsigned long long lo = kmin, hi = kmax;
+        int need = kp, n_above = 0, take_eq = 0;
+        const int per = RR_FIN_BINS / n_threads;  // bins per thread in the suffix scan (4 or 8)
+        for (;;) {
+            const unsigned long long range = hi - lo;
+            const int sh = max(0, (64 - __clzll((long long)(range | 1ull))) - RR_FIN_BINS_LOG2);
+            for (int i = tid; i < RR_FIN_BINS; i += n_threads) hist[i] = 0;
             __syncthreads();
-            const unsigned long long prefix = s_prefix, mask = s_mask;
-            // warp-aggregated counting: candidate scores cluster (same sign and exponent), so in the leading
-            // passes nearly every lane hits the same bin and plain shared-memory atomics would serialise
-            for (int i0 = 0; i0 < n_cand; i0 += n_threads) {
-                const int i = i0 + tid;
-                uint32_t digit = 0;
-                bool in = false;
-                if (i < n_cand) {
-                    const uint32_t r = cr[i];
-                    if (r != RR_NO_ROW) {
-                        unsigned long long key = rr_float_key(cs[i]);
-                        if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
-                        in = (key & mask) == prefix;
-                        digit = (uint32_t)((key >> shift) & 0xFFull);
-                    }
-                }
-                const unsigned live = __ballot_sync(RR_FULL, in);
-                if (in) {
-                    const unsigned peers = __match_any_sync(live, digit);
-                    if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
-                }
+            for (int i = tid; i < n_cand; i += n_threads) {
+                const uint32_t r = cr[i];
+                if (r == RR_NO_ROW) continue;
+                const unsigned long long key = key_of(cs[i], r);
+                if (key >= lo && key <= hi) atomicAdd(&hist[(uint32_t)((key - lo) >> sh)], 1u);
             }
             __syncthreads();
-            if (w == 0) {
-                // lane L owns digits 255-8L .. 248-8L (descending)
-                const uint32_t rem = (uint32_t)s_remaining;
-                __syncwarp();
-                uint32_t c[8];
-                uint32_t tot = 0;
+            // thread t owns bins RR_FIN_BINS - 1 - t * per ... downwards; inclusive scan of the thread totals
+            uint32_t c[8];
+            uint32_t tot = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                c[j] = (j < per) ? hist[RR_FIN_BINS - 1 - (tid * per + j)] : 0u;
+                tot += c[j];
+            }
+            uint32_t incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(RR_FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (lane == 31) s_scan[w] = incl;
+            __syncthreads();
+            uint32_t before = 0;
+            for (int i = 0; i < w; ++i) before += s_scan[i];
+            incl += before;
+            const uint32_t excl = incl - tot;
+            if (excl < (uint32_t)need && (uint32_t)need <= incl) {  // exactly one thread
+                uint32_t run = excl;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    c[j] = hist[255 - (lane * 8 + j)];
-                    tot += c[j];
-                }
-                uint32_t incl = tot;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t v = __shfl_up_sync(RR_FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                const uint32_t excl = incl - tot;
-                if (excl < rem && rem <= incl) {  // exactly one lane
-                    uint32_t run = excl;
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (run < rem && rem <= run + c[j]) {
-                            const unsigned long long digit = 255 - (lane * 8 + j);
-                            s_prefix = prefix | (digit << shift);
-                            s_mask = mask | (0xFFull << shift);
-                            s_remaining = (int)(rem - run);
-                        }
-                        run += c[j];
+                    if (j < per && run < (uint32_t)need && (uint32_t)need <= run + c[j]) {
+                        s_bstar = RR_FIN_BINS - 1 - (tid * per + j);
+                        s_cgt = (int)run;
+                        s_ceq = (int)c[j];
                     }
+                    run += c[j];
                 }
             }
             __syncthreads();
+            const int bstar = s_bstar, cgt = s_cgt, ceq = s_ceq;
+            const unsigned long long wlo = lo + ((unsigned long long)bstar << sh);
+            const unsigned long long whi = min(hi, wlo + ((1ull << sh) - 1ull));
+            n_above += cgt;
+            need -= cgt;
+            lo = wlo;
+            hi = whi;
+            if (n_above + ceq <= RR_FIN_MAXSEL) {  // the whole boundary bin fits
+                take_eq = ceq;
+                break;
+            }
+            if (sh == 0) {  // one key value, more copies than fit: equal keys, any `need` of them will do
+                take_eq = need;
+                break;
+            }
+            __syncthreads();  // s_bstar / hist are rewritten by the next level
         }
-        // gather: keys above the kp-th all go in; equal keys fill the remaining slots
-        const unsigned long long kth = s_prefix;
-        const int n_eq_take = s_remaining;
-        const int n_gt = kp - n_eq_take;
-        for (int i = tid; i < n_cand; i += blockDim.x) {
+        // gather: keys above the window all go in, the window's keys fill the remaining slots
+        for (int i = tid; i < n_cand; i += n_threads) {
             const uint32_t r = cr[i];
             if (r == RR_NO_ROW) continue;
-            const float s = cs[i];
-            unsigned long long key = rr_float_key(s);
-            if (!RESCORE) key = (key << 32) | (unsigned long long)(~r);
-            if (key > kth) {
+            const float sc = cs[i];
+            const unsigned long long key = key_of(sc, r);
+            if (key > hi) {
                 const int p = atomicAdd(&s_cnt_gt, 1);
-                sel_s[p] = s;
+                sel_s[p] = sc;
                 sel_r[p] = r;
-            } else if (key == kth) {
+            } else if (key >= lo) {
                 const int p = atomicAdd(&s_cnt_eq, 1);
-                if (p < n_eq_take) {
-                    sel_s[n_gt + p] = s;
-                    sel_r[n_gt + p] = r;
+                if (p < take_eq) {
+                    sel_s[n_above + p] = sc;
+                    sel_r[n_above + p] = r;
                 }
             }
         }
-        if (n_valid > kp) t_rest = rr_key_float((uint32_t)(RESCORE ? kth : (kth >> 32)));
+        kp = n_above + take_eq;  // what was selected: >= the kp asked for
+        if (n_valid > kp) {
+            // every unselected candidate's key is below the window (or, when equal keys were cut, inside it)
+            const unsigned long long edge = (take_eq < (int)s_ceq) ? lo : (lo > 0 ? lo - 1 : 0);
+            const uint32_t e32 = (uint32_t)(RESCORE ? edge : (edge >> 32));
+            t_rest = e32 ? rr_key_float(e32) : RR_NEG_INF;
+        }
     }
     // pad the selection to a power of two for the sort
     int kp_pad = 1;
@@ -771,6 +892,7 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
 template <bool RESCORE, bool BIG>
 __global__ void __launch_bounds__(BIG ? RR_FIN_THREADS / 2 : RR_FIN_THREADS, BIG ? 4 : 1)
 rr_finalize_kernel(const __grid_constant__ rr_multi<rr_finalize_args> m) {
+    rr_pdl_enter();
     const rr_finalize_args& a = m.s[blockIdx.y];
     if (!a.enabled) return;
     constexpr int CH = BIG ? 1 : 3;
@@ -808,6 +930,7 @@ struct rr_prep_collect_args {
 
 __global__ void __launch_bounds__(128)
 rr_prep_collect_kernel(const __grid_constant__ rr_multi<rr_prep_collect_args> m) {
+    rr_pdl_enter();
     const rr_prep_collect_args& a = m.s[blockIdx.y];
     if (a.nq_pad2 == 0) return;
     const int d_pad = a.d_pad;
@@ -958,6 +1081,7 @@ __device__ __forceinline__ void rr_finalize_collect_one(const rr_collect_fin_arg
 // grid = (a few blocks, sources): the blocks stride over the failing queries (normally none)
 __global__ void __launch_bounds__(RR_FIN_THREADS)
 rr_finalize_collect_kernel(const __grid_constant__ rr_multi<rr_collect_fin_args> m) {
+    rr_pdl_enter();
     const rr_collect_fin_args& a = m.s[blockIdx.y];
     if (!a.enabled) return;
     const int n_fail = a.ctl->n_fail;
@@ -1179,6 +1303,9 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
         RR_REQUIRE(value == RR_PATH_AUTO || value == RR_PATH_SMALL || value == RR_PATH_GEMM || value == RR_PATH_GEMM_PAIR,
                    "scan_path must be 0 (auto), 1 (64-query passes), 2 (large-batch kernel) or 3 (large-batch, CTA pairs)");
         h->scan_path = (int)value;
+    } else if (!strcmp(name, "gemm_depth")) {
+        RR_REQUIRE(value == 0 || value == 8 || value == 32, "gemm_depth must be 0 (automatic), 8 or 32");
+        h->gemm_depth = (int)value;
     } else if (!strcmp(name, "gemm_tmem_all")) {
         h->gemm_tmem_all = value != 0;
     } else {
@@ -1443,11 +1570,14 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         a.compact = p.use_gemm ? 1 : 0;
     }
     if (do_first) {
-        rr_begin_chunk_kernel<<<S, 1024, 0, stream>>>(pa);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_prep_queries_kernel<<<dim3((unsigned)max_nq_pad, (unsigned)S), 128, 0, stream>>>(pa);
-        RR_CUDA_CHECK(cudaGetLastError());
-        rr_count_launch(2);
+        if (max_nq_pad <= RR_FUSED_PREP_MAX) {
+            RR_CUDA_CHECK(rr_launch_pdl(rr_begin_prep_fused_kernel, dim3((unsigned)S), dim3(1024), 0, stream, pa));
+            rr_count_launch(1);
+        } else {
+            RR_CUDA_CHECK(rr_launch_pdl(rr_begin_chunk_kernel, dim3((unsigned)S), dim3(1024), 0, stream, pa));
+            RR_CUDA_CHECK(rr_launch_pdl(rr_prep_queries_kernel, dim3((unsigned)max_nq_pad, (unsigned)S), dim3(128), 0, stream, pa));
+            rr_count_launch(2);
+        }
     }
 
     rr_multi<rr_finalize_args> fa;
@@ -1514,7 +1644,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             a.n_lists = 0;
             a.lists_from_ctl = 1;
             a.cpos = p.cpos;
-            a.depth = RR_GEMM_LIST_DEPTH;
+            a.depth = rr_gemm_scan_list_depth(h);
         } else if (p.use_tc) {
             for (int p0 = 0; p0 < nq; p0 += p.qt) {
                 const int nqt = std::min(p.qt, nq - p0);
@@ -1535,9 +1665,9 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         if (rc != RR_OK) return rc;
     }
     if (any_first) {
-        if (fin_small) rr_finalize_kernel<true, false><<<dim3((unsigned)nq, (unsigned)S), fin_threads, fin_smem[1], stream>>>(fa);
-        else rr_finalize_kernel<true, true><<<dim3((unsigned)nq, (unsigned)S), fin_threads, fin_smem[1], stream>>>(fa);
-        RR_CUDA_CHECK(cudaGetLastError());
+        const dim3 g1((unsigned)nq, (unsigned)S);
+        if (fin_small) RR_CUDA_CHECK(rr_launch_pdl(rr_finalize_kernel<true, false>, g1, dim3(fin_threads), fin_smem[1], stream, fa));
+        else RR_CUDA_CHECK(rr_launch_pdl(rr_finalize_kernel<true, true>, g1, dim3(fin_threads), fin_smem[1], stream, fa));
         rr_count_launch(1);
     }
     }  // do_first
@@ -1588,8 +1718,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             c.out_stride = p.out_stride;
             c.enabled = 1;
         }
-        rr_prep_collect_kernel<<<dim3((unsigned)std::min(max_nq_pad2, 256), (unsigned)S), 128, 0, stream>>>(pc);
-        RR_CUDA_CHECK(cudaGetLastError());
+        RR_CUDA_CHECK(rr_launch_pdl(rr_prep_collect_kernel, dim3((unsigned)std::min(max_nq_pad2, 256), (unsigned)S), dim3(128), 0,
+                                    stream, pc));
         rr_count_launch(1);
         int n_collect = 0;
         for (int s = 0; s < S; ++s) {
@@ -1606,9 +1736,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             ++n_collect;
             rr_count_launch(p.cg2 == 0 ? 2 : 1);
         }
-        rr_finalize_collect_kernel<<<dim3((unsigned)fin_blocks_sparse, (unsigned)S), RR_FIN_THREADS,
-                                     (size_t)max_dpad * sizeof(float), stream>>>(cf);
-        RR_CUDA_CHECK(cudaGetLastError());
+        RR_CUDA_CHECK(rr_launch_pdl(rr_finalize_collect_kernel, dim3((unsigned)fin_blocks_sparse, (unsigned)S),
+                                    dim3(RR_FIN_THREADS), (size_t)max_dpad * sizeof(float), stream, cf));
         rr_count_launch(1);
     }
 
@@ -1641,8 +1770,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         const int g_exact = plans[0].g_exact;
         const int gy = any_first ? 1 : std::min(4, (nq + min_qsub - 1) / min_qsub);
         const dim3 grid((unsigned)g_exact, (unsigned)gy, (unsigned)S);
-        rr_exact_scan_kernel<RR_EXACT_MAX_QSUB><<<grid, RR_EXACT_WARPS * 32, max_ex_smem, stream>>>(ea);
-        RR_CUDA_CHECK(cudaGetLastError());
+        RR_CUDA_CHECK(rr_launch_pdl(rr_exact_scan_kernel<RR_EXACT_MAX_QSUB>, grid, dim3(RR_EXACT_WARPS * 32), max_ex_smem, stream, ea));
         rr_count_launch(1);
     }
     // after a tensor-core pass only the queries the second pass could not settle are left (normally none):
@@ -1666,9 +1794,8 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
         }
     }
     const dim3 fgrid((unsigned)(all_sparse ? fin_blocks_sparse : nq), (unsigned)S);
-    if (fin_small) rr_finalize_kernel<false, false><<<fgrid, fin_threads, fin_smem[0], stream>>>(fa);
-    else rr_finalize_kernel<false, true><<<fgrid, fin_threads, fin_smem[0], stream>>>(fa);
-    RR_CUDA_CHECK(cudaGetLastError());
+    if (fin_small) RR_CUDA_CHECK(rr_launch_pdl(rr_finalize_kernel<false, false>, fgrid, dim3(fin_threads), fin_smem[0], stream, fa));
+    else RR_CUDA_CHECK(rr_launch_pdl(rr_finalize_kernel<false, true>, fgrid, dim3(fin_threads), fin_smem[0], stream, fa));
     rr_count_launch(1);
     return RR_OK;
 }
@@ -1940,7 +2067,6 @@ extern "C" int rr_normalize_l2(float* x_dev, int64_t n, int d, void* stream) {
     if (n == 0) return RR_OK;
     RR_REQUIRE(x_dev != nullptr, "rr_normalize_l2: NULL buffer");
     RR_REQUIRE(n <= 0x7FFFFFFF, "rr_normalize_l2: too many rows");
-    rr_normalize_l2_kernel<<<(unsigned)n, 128, 0, (cudaStream_t)stream>>>(x_dev, n, d);
-    RR_CUDA_CHECK(cudaGetLastError());
+    RR_CUDA_CHECK(rr_launch_pdl(rr_normalize_l2_kernel, dim3((unsigned)n), dim3(128), 0, (cudaStream_t)stream, x_dev, n, d));
     return RR_OK;
 }

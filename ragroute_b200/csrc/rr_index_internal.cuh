@@ -45,6 +45,7 @@ struct rr_index {
     int kprime = 128;
     int profile = 0;
     int scan_path = RR_PATH_AUTO;
+    int gemm_depth = 0;     // 0 = automatic list depth of the queries-in-TMEM scan (8 for small shards, else 32)
     int gemm_tmem_all = 1;  // <= 128 queries: whole query tile in TMEM, one accumulator stage (testing knob)
 
     // per-search scratch (grow-only)
@@ -121,6 +122,7 @@ int rr_make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int 
 // the number of slices in ctl->n_lists.
 bool rr_gemm_scan_supported(const rr_index* h);
 int rr_gemm_scan_max_lists(const rr_index* h);
+int rr_gemm_scan_list_depth(const rr_index* h);  // entries per (corpus slice, query) list for this index: 8 or 32
 // cta_group: 1 = one CTA per 128-query tile; 2 = CTA pairs (cluster of 2, 256 queries per pair),
 // for which qbf16 holds ceil(nq / 256) * 256 rows.
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,

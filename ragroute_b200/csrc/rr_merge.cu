@@ -65,6 +65,7 @@ __device__ __forceinline__ void lane_best(const MergeArgs& a, int64_t b, const u
 }
 
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(const MergeArgs a) {
+    rr_pdl_enter();  // see rr_common.cuh: the step's kernels overlap their launch gaps
     extern __shared__ uint32_t keys_all[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + w;
@@ -142,8 +143,7 @@ int merge_launch(const MergeArgs& a, cudaStream_t stream) {
                                            (int)smem));
     }
     const unsigned blocks = (unsigned)((a.B + kWarpsPerBlock - 1) / kWarpsPerBlock);
-    rr_merge_topk_kernel<<<blocks, kWarpsPerBlock * 32, smem, stream>>>(a);
-    RR_CUDA_CHECK(cudaGetLastError());
+    RR_CUDA_CHECK(rr_launch_pdl(rr_merge_topk_kernel, dim3(blocks), dim3(kWarpsPerBlock * 32), smem, stream, a));
     rr_count_launch(1);
     return RR_OK;
 }

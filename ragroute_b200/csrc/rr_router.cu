@@ -10,6 +10,7 @@
 // The scaler is applied exactly as the reference does: (x - mean_) / scale_ in
 // float64, then cast to fp32 (router.py:270-271).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <new>
@@ -29,6 +30,13 @@ constexpr int kPG = 16;               // (query, source) pairs per fc2 round
 constexpr int kHStride = kPG + 4;     // h1t row pitch: float4-aligned, spreads the transposing stores over banks
 constexpr int kInFlight = 16;         // independent weight loads per thread (the loops are L2-latency-bound)
 constexpr float kLnEps = 1e-5f;
+// fc1 is summed in a FIXED tree whatever the launch shape, so that a query's logits do not depend on the batch
+// it arrives in: the input dimensions are cut into kKE x kKQ contiguous slices, each accumulated in ascending
+// order; per K-quarter kq the slices e = 0 .. kKE-1 are added in ascending order, then the quarters.
+// Small batches run one thread-block CLUSTER of kKE CTAs per kQB queries, CTA e taking slices (e, *): one SM
+// pulling fc1's 786 KB through a single L1 was 2/3 of the kernel's 33 us at batch 1 (ncu, round 2).
+constexpr int kKE = 8;
+constexpr int kClusterMaxBatch = 128;  // above this the grid fills the SMs without clusters
 }  // namespace
 
 struct rr_router {
@@ -81,26 +89,47 @@ struct RouterArgs {
     float* logits;            // [B][S] or null
 };
 
+__device__ __forceinline__ uint32_t router_cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void router_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store into the same shared-memory variable of the cluster's CTA 0
+__device__ __forceinline__ void router_store_leader(float* p, float v) {
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(p), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(v) : "memory");
+}
+
 // Shared memory: [ xq | part ] is dead once fc1 is done and is reused for the fc2 partial sums.
+// CL = 1: one CTA per kQB queries.  CL = kKE: a cluster per kQB queries; CTA e computes the fc1 slices (e, *)
+// and ships them to CTA 0 (distributed shared memory), which finishes the network alone.
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1) rr_router_kernel(const RouterArgs a) {
+    rr_pdl_enter();  // see rr_common.cuh: the step's kernels overlap their launch gaps
+    if (CL > 1) router_cluster_sync();  // every CTA of the cluster runs before its shared memory is written remotely
     extern __shared__ __align__(16) float sm[];
     const size_t n_x = ((size_t)kQB * a.d_in + 3) & ~(size_t)3;
-    const size_t n_u = max(n_x + (size_t)kKQ * kQB * kH1, (size_t)kKS * kPG * kH2);
+    const size_t n_p1 = (CL > 1) ? (size_t)kKE * kKQ * kQB * kH1 : (size_t)kKQ * kQB * kH1;
+    const size_t n_u = max(n_x + n_p1, (size_t)kKS * kPG * kH2);
     float* xq = sm;                                   // [kQB][d_in]
-    float* part = xq + n_x;                           // [kKQ][kQB][256]
+    float* part = xq + n_x;                           // [kKQ][kQB][256]  (CL > 1, leader: [kKE][kKQ][kQB][256])
     float* part2 = sm;                                // [kKS][kPG][128]   (aliases xq / part)
     float* g = sm + n_u;                              // [n_slots][kQB][256]
     float* h1t = g + (size_t)a.n_slots * kQB * kH1;   // [256][kHStride]: relu(ln1(fc1)) of kPG pairs, transposed
 
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const int64_t b0 = (int64_t)blockIdx.x * kQB;
+    const int crank = (CL > 1) ? (int)router_cluster_rank() : 0;
+    const int64_t b0 = (int64_t)(blockIdx.x / CL) * kQB;
     const int nqb = (int)min((int64_t)kQB, a.B - b0);
 
     // ---- phase 1: g[slot][qb][:] = W1[:, :d_in] . scaled(x[qb][slot][:]) ----
     const int t = tid & (kH1 - 1);
     const int kq = tid >> 8;
-    const int j_lo = (int)((int64_t)kq * a.d_in / kKQ);
-    const int j_hi = (int)((int64_t)(kq + 1) * a.d_in / kKQ);
     for (int sl = 0; sl < a.n_slots; ++sl) {
         for (int i = tid; i < kQB * a.d_in; i += kThreads) {
             const int qb = i / a.d_in, j = i - qb * a.d_in;
@@ -112,37 +141,85 @@ __global__ void __launch_bounds__(kThreads, 1) rr_router_kernel(const RouterArgs
             xq[i] = v;
         }
         __syncthreads();
-        float acc[kQB];
+        float tot[kQB];
 #pragma unroll
-        for (int qb = 0; qb < kQB; ++qb) acc[qb] = 0.f;
+        for (int qb = 0; qb < kQB; ++qb) tot[qb] = 0.f;
         const float* wp = a.w1t + t;
-        int j = j_lo;
-        for (; j + kInFlight <= j_hi; j += kInFlight) {
-            float wv[kInFlight];
+        for (int e = (CL > 1 ? crank : 0); e < (CL > 1 ? crank + 1 : kKE); ++e) {
+            const int slice = e * kKQ + kq;
+            const int j_lo = (int)((int64_t)slice * a.d_in / (kKE * kKQ));
+            const int j_hi = (int)((int64_t)(slice + 1) * a.d_in / (kKE * kKQ));
+            float acc[kQB];
 #pragma unroll
-            for (int u = 0; u < kInFlight; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
+            for (int qb = 0; qb < kQB; ++qb) acc[qb] = 0.f;
+            int j = j_lo;
+            for (; j + kInFlight <= j_hi; j += kInFlight) {
+                float wv[kInFlight];
 #pragma unroll
-            for (int qb = 0; qb < kQB; ++qb) {
-                const float* xr = xq + (size_t)qb * a.d_in + j;
+                for (int u = 0; u < kInFlight; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
 #pragma unroll
-                for (int u = 0; u < kInFlight; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
+                for (int qb = 0; qb < kQB; ++qb) {
+                    const float* xr = xq + (size_t)qb * a.d_in + j;
+#pragma unroll
+                    for (int u = 0; u < kInFlight; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
+                }
+            }
+            if (j + kInFlight / 2 <= j_hi) {
+                float wv[kInFlight / 2];
+#pragma unroll
+                for (int u = 0; u < kInFlight / 2; ++u) wv[u] = __ldg(wp + (size_t)(j + u) * kH1);
+#pragma unroll
+                for (int qb = 0; qb < kQB; ++qb) {
+                    const float* xr = xq + (size_t)qb * a.d_in + j;
+#pragma unroll
+                    for (int u = 0; u < kInFlight / 2; ++u) acc[qb] = fmaf(wv[u], xr[u], acc[qb]);
+                }
+                j += kInFlight / 2;
+            }
+            for (; j < j_hi; ++j) {
+                const float w0 = __ldg(wp + (size_t)j * kH1);
+#pragma unroll
+                for (int qb = 0; qb < kQB; ++qb) acc[qb] = fmaf(w0, xq[(size_t)qb * a.d_in + j], acc[qb]);
+            }
+            if (CL > 1) {
+#pragma unroll
+                for (int qb = 0; qb < kQB; ++qb)
+                    router_store_leader(part + ((size_t)(e * kKQ + kq) * kQB + qb) * kH1 + t, acc[qb]);
+            } else {
+#pragma unroll
+                for (int qb = 0; qb < kQB; ++qb) tot[qb] += acc[qb];
             }
         }
-        for (; j < j_hi; ++j) {
-            const float w0 = __ldg(wp + (size_t)j * kH1);
+        if (CL > 1) {
+            router_cluster_sync();  // every CTA's slices have landed in the leader's shared memory
+            if (crank == 0) {
+                for (int i = tid; i < kQB * kH1; i += kThreads) {
+                    float v = 0.f;
 #pragma unroll
-            for (int qb = 0; qb < kQB; ++qb) acc[qb] = fmaf(w0, xq[(size_t)qb * a.d_in + j], acc[qb]);
+                    for (int c = 0; c < kKQ; ++c) {
+                        float tq = 0.f;
+#pragma unroll
+                        for (int e = 0; e < kKE; ++e) tq += part[((size_t)(e * kKQ + c) * kQB) * kH1 + i];
+                        v = (c == 0) ? tq : v + tq;
+                    }
+                    g[(size_t)sl * kQB * kH1 + i] = v;
+                }
+            }
+            if (sl + 1 < a.n_slots) router_cluster_sync();  // the leader has read them: the next slot may overwrite
+            else if (crank != 0) return;                    // only the leader goes on
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int qb = 0; qb < kQB; ++qb) part[(kq * kQB + qb) * kH1 + t] = tot[qb];
+            __syncthreads();
+            for (int i = tid; i < kQB * kH1; i += kThreads) {
+                float v = part[i];
+#pragma unroll
+                for (int c = 1; c < kKQ; ++c) v += part[c * kQB * kH1 + i];
+                g[(size_t)sl * kQB * kH1 + i] = v;
+            }
+            __syncthreads();
         }
-#pragma unroll
-        for (int qb = 0; qb < kQB; ++qb) part[(kq * kQB + qb) * kH1 + t] = acc[qb];
-        __syncthreads();
-        for (int i = tid; i < kQB * kH1; i += kThreads) {
-            float v = part[i];
-#pragma unroll
-            for (int c = 1; c < kKQ; ++c) v += part[c * kQB * kH1 + i];
-            g[(size_t)sl * kQB * kH1 + i] = v;
-        }
-        __syncthreads();
     }
 
     // ---- phase 2: (query, source) pairs, kPG at a time ----
@@ -265,21 +342,43 @@ int upload(T** dst, const T* src, size_t n) {
     return RR_OK;
 }
 
-size_t router_smem(int d_in, int n_slots) {
+size_t router_smem(int d_in, int n_slots, int cl) {
     const size_t n_x = ((size_t)kQB * d_in + 3) & ~(size_t)3;
-    const size_t n_u = std::max(n_x + (size_t)kKQ * kQB * kH1, (size_t)kKS * kPG * kH2);
+    const size_t n_p1 = (cl > 1) ? (size_t)kKE * kKQ * kQB * kH1 : (size_t)kKQ * kQB * kH1;
+    const size_t n_u = std::max(n_x + n_p1, (size_t)kKS * kPG * kH2);
     return (n_u + (size_t)n_slots * kQB * kH1 + (size_t)kH1 * kHStride) * sizeof(float);
 }
 
+template <int CL>
+int router_launch_cl(const RouterArgs& a, size_t smem, cudaStream_t stream) {
+    RR_CUDA_CHECK(cudaFuncSetAttribute(rr_router_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((a.B + kQB - 1) / kQB) * CL);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = rr_pdl_enabled() ? 2 : 1;
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_router_kernel<CL>, a));
+    return RR_OK;
+}
+
 int router_launch(rr_router* h, const RouterArgs& a, cudaStream_t stream) {
-    const size_t smem = router_smem(a.d_in, a.n_slots);
+    // small batches: a cluster of kKE CTAs per kQB queries shares fc1 (when the leader's staging fits)
+    static const bool no_cluster = getenv("RR_ROUTER_NO_CLUSTER") != nullptr;  // measurement knob
+    const bool cluster = !no_cluster && a.B <= kClusterMaxBatch && router_smem(a.d_in, a.n_slots, kKE) <= (size_t)227 * 1024;
+    const size_t smem = router_smem(a.d_in, a.n_slots, cluster ? kKE : 1);
     RR_REQUIRE(smem <= (size_t)227 * 1024, "router: %zu bytes of shared memory needed (d_in=%d, slots=%d)",
                smem, a.d_in, a.n_slots);
-    RR_CUDA_CHECK(cudaFuncSetAttribute(rr_router_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       227 * 1024));
-    const unsigned blocks = (unsigned)((a.B + kQB - 1) / kQB);
-    rr_router_kernel<<<blocks, kThreads, smem, stream>>>(a);
-    RR_CUDA_CHECK(cudaGetLastError());
+    int rc = cluster ? router_launch_cl<kKE>(a, smem, stream) : router_launch_cl<1>(a, smem, stream);
+    if (rc != RR_OK) return rc;
     rr_count_launch(1);
     (void)h;
     return RR_OK;

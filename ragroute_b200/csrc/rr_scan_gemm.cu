@@ -34,6 +34,8 @@
 // a slice stream the same rows at the same time, so HBM is read once and the other
 // nqt - 1 reads hit L2.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc), 2..5 = A loader + epilogue.
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 
@@ -78,10 +80,28 @@ struct GemmParams {
     int* col_cnt;           // [compact query] (may exceed col_cap: overflow, the caller falls back)
     int col_cap;
     int min_active, max_active;  // run only if min_active <= routed queries <= max_active (see rr_gemm_scan_launch)
+    int chained;                 // 1: directly follows another scan of the same step (PDL, see rr_scan_tc.cu)
+    int trace;                   // RR_TRACE: block 0 records a timeline (debugging aid)
     float* cand_s;  // [compact query][slice][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
 };
+
+// Timeline tracing (debugging aid, RR_TRACE=1 in the environment): block 0 records (tag, tile, globaltimer) events
+// of its three roles into a device array that rr_debug_read_trace copies out.  Off: one predictable branch.
+constexpr int kTraceCap = 4096;
+__device__ unsigned long long g_trace[kTraceCap * 2];
+__device__ unsigned int g_trace_n;
+__device__ __forceinline__ void trace_ev(int on, int tag, int tile) {
+    if (!on) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    const unsigned i = atomicAdd(&g_trace_n, 1u);
+    if (i < kTraceCap) {
+        g_trace[2 * i] = ((unsigned long long)tag << 32) | (unsigned)tile;
+        g_trace[2 * i + 1] = t;
+    }
+}
 
 // Per-thread state: unsorted top-kDepth list of the thread's query in shared memory, entry e of
 // thread t at [e * kQTile + t] (conflict-free across a warp); `thr` = the list's minimum score
@@ -98,6 +118,7 @@ __device__ __noinline__ void epi_collect(int cnt, int qg, const GemmParams& p, c
     }
 }
 
+template <int DEPTH>
 __device__ __noinline__ void epi_drain(int cnt, float& thr, int& pos, float* ls, uint32_t* lr, const float* ps,
                                        const uint32_t* pr, int t) {
     int i = 0;
@@ -107,18 +128,40 @@ __device__ __noinline__ void epi_drain(int cnt, float& thr, int& pos, float* ls,
             if (v > thr) {  // an earlier insert of this drain may have raised the threshold
                 ls[pos * kQTile + t] = v;
                 lr[pos * kQTile + t] = pr[i * kQTile + t];
-                float m = ls[t];
-                int am = 0;
+                // new minimum of the list: four independent chains (a single chain of DEPTH - 1 dependent
+                // compare-selects made a round cost ~900 cycles: measured with RR_TRACE on a 125 k-row corpus)
+                float m[4];
+                int am[4];
 #pragma unroll
-                for (int e = 1; e < kDepth; ++e) {
-                    const float sv = ls[e * kQTile + t];
-                    if (sv < m) {
-                        m = sv;
-                        am = e;
+                for (int c = 0; c < 4; ++c) {
+                    m[c] = ls[c * kQTile + t];
+                    am[c] = c;
+                }
+#pragma unroll
+                for (int e = 4; e < DEPTH; e += 4) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float sv = ls[(e + c) * kQTile + t];
+                        if (sv < m[c]) {
+                            m[c] = sv;
+                            am[c] = e + c;
+                        }
                     }
                 }
-                thr = m;
-                pos = am;
+                if (m[1] < m[0]) {
+                    m[0] = m[1];
+                    am[0] = am[1];
+                }
+                if (m[3] < m[2]) {
+                    m[2] = m[3];
+                    am[2] = am[3];
+                }
+                if (m[2] < m[0]) {
+                    m[0] = m[2];
+                    am[0] = am[2];
+                }
+                thr = m[0];
+                pos = am[0];
             }
         }
         ++i;
@@ -133,14 +176,19 @@ static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA b
 //         CTA, each in its own TMEM) against the same 128-row corpus tiles, of which each CTA
 //         streams only 64 rows -- per SM half the L2->smem traffic and half the shared-memory
 //         operand reads per flop, which is what bounds CG = 1.
-// COLLECT = false: per-query top-32 lists (first pass).  COLLECT = true: fixed per-query thresholds, every
+// COLLECT = false: per-query top-DEPTH lists (first pass).  COLLECT = true: fixed per-query thresholds, every
 // row above them is reported (second pass for the queries whose certificate failed).
-template <int CG, bool COLLECT>
+// DEPTH = entries per (corpus slice, query) list: 32 for large shards; 8 for small ones (<= ~16 k rows per
+// list), where a cold list of 32 lets ~32 (1 + ln(rows / 32)) rows through the insert path -- ~170 SIMT rounds
+// per warp on a 125 k-row corpus, 80 us of a launch whose HBM time is 29 us (RR_TRACE timeline) -- while
+// 148 lists x 8 still hold far more than the k' = 128 candidates the finalize wants.
+template <int CG, bool COLLECT, int DEPTH>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                     const GemmParams p) {
     // Work split, decided on the device from the number of ROUTED queries: nqt query tiles of
     // 128 * CG (compacted, so unrouted queries cost nothing) x n_slices corpus slices.
+    if (!p.chained) pdl_wait_primary();  // first scan of a chain: the query preparation before it must be complete
     pdl_launch_dependents();  // the next scan of the step may take SMs as they free up
     const int n_active = p.ctl->n_active;
     // no query routed to this source: do not touch the corpus; outside [min_active, max_active]: the launch of
@@ -194,6 +242,8 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const int tr = (p.trace && blockIdx.x == 0 && lane == 0) ? 1 : 0;
+    trace_ev(tr && warp == 0, 0, 0);  // kernel start
 
     // Barrier protocol for a pair (CG = 2): the LEADER owns bar_full (armed by its producer with the
     // bytes of both CTAs; both producers' TMA complete on it), bar_acc_empty and bar_a (both CTAs'
@@ -252,6 +302,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
                 const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
+                trace_ev(tr && kc == 0, 1, tile);  // producer: first stage of the tile is free
                 if (elect_one_sync()) {
                     if (CG == 2) {
                         const uint32_t full_leader = mapa_shared(smem_u32(bar_full + stage), 0);
@@ -279,6 +330,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (rank == 0) {  // only the leader of a pair issues
         mbar_wait(smem_u32(bar_a), 0);  // the query tiles are in TMEM and their tails in shared memory
         tc_fence_after();
+        trace_ev(tr, 2, 0);  // MMA warp: query tile in place
         int stage = 0, acc = 0;
         uint32_t phase = 0, acc_phase = 0;
         const uint32_t x_base = smem_u32(x_sm);
@@ -286,11 +338,13 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             mbar_wait(smem_u32(bar_acc_empty + acc), acc_phase ^ 1u);
             tc_fence_after();
+            trace_ev(tr, 3, tile);  // MMA warp: accumulator free
             const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
             for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
                 const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
+                trace_ev(tr && (kc == 0 || kc + kStageKc >= p.num_kc), 4, tile);  // MMA warp: first / last stage of the tile landed
                 const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageB) >> 4) & 0x3FFFu);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(kc * 32);
                 const uint64_t a_desc =
@@ -364,27 +418,39 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         const int qg = qt * kQTile + t;      // query inside the chunk
         const uint32_t lane_addr = tmem_base + ((uint32_t)(quad * 32) << 16);
         {
-            // each thread copies its own query row (a_cols * 4 bytes) into its TMEM lane; 16 x 16-byte
-            // loads in flight per thread (a_cols is a multiple of 32: whole K-chunks) -- nothing streams
-            // until the tile is in place, so this latency is paid once per launch by the whole SM
-            const uint4* src = reinterpret_cast<const uint4*>(p.qbf16 + (size_t)qg * p.d_pad);
-            for (uint32_t c = 0; c < a_cols; c += 64) {
+            // The warp's 32 query rows go into its 32 TMEM lanes, a_cols * 4 bytes each.  tcgen05.st wants row i in
+            // the registers of lane i, but a lane reading its own row straight from global memory makes every load
+            // instruction touch 32 different lines (9 us for the tile, RR_TRACE).  So: coalesced loads (half a warp
+            // per 256-byte row piece), a transpose through shared memory (the list / pending arrays, not yet in
+            // use: 32 rows x (256 + 16) bytes per warp), and each lane picks up its own row.
+            constexpr int kPitch = 272;  // bytes per staged row piece: conflict-free 16-byte reads of one's own row
+            static_assert(4 * 32 * kPitch <= (kDepth + kPend) * kQTile * 8, "staging aliases the list arrays");
+            uint8_t* stg = reinterpret_cast<uint8_t*>(ls) + quad * (32 * kPitch);
+            const uint8_t* tile0 = reinterpret_cast<const uint8_t*>(p.qbf16 + (size_t)(qt * kQTile + quad * 32) * p.d_pad);
+            const size_t row_bytes = (size_t)p.d_pad * 2;
+            const int half = lane >> 4, l16 = lane & 15;
+            for (uint32_t c = 0; c < a_cols; c += 64) {  // 64 TMEM columns = 256 bytes of every row
+                const bool two = c + 32 < a_cols;  // (a_cols is a multiple of 32: the last piece may be 128 bytes)
                 uint4 v[16];
-                const bool two = c + 32 < a_cols;
+                if (two || l16 < 8) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (c >> 2) + u);
-                if (two) {
+                    for (int u = 0; u < 16; ++u)
+                        v[u] = __ldg(reinterpret_cast<const uint4*>(tile0 + (size_t)(2 * u + half) * row_bytes + 4 * c) + l16);
 #pragma unroll
-                    for (int u = 8; u < 16; ++u) v[u] = __ldg(src + (c >> 2) + u);
+                    for (int u = 0; u < 16; ++u)
+                        *reinterpret_cast<uint4*>(stg + (2 * u + half) * kPitch + 16 * l16) = v[u];
                 }
+                __syncwarp();
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     if (u < 4 || two) {
-                        const uint32_t r[8] = {v[2 * u].x, v[2 * u].y, v[2 * u].z, v[2 * u].w,
-                                               v[2 * u + 1].x, v[2 * u + 1].y, v[2 * u + 1].z, v[2 * u + 1].w};
+                        const uint4 lo4 = *reinterpret_cast<const uint4*>(stg + lane * kPitch + 32 * u);
+                        const uint4 hi4 = *reinterpret_cast<const uint4*>(stg + lane * kPitch + 32 * u + 16);
+                        const uint32_t r[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
                         tmem_st_x8(lane_addr + c + 8 * u, r);
                     }
                 }
+                __syncwarp();  // the staging rows are rewritten by the next piece
             }
             tmem_st_wait();
             tc_fence_before();
@@ -393,8 +459,9 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 if (CG == 2) mbar_arrive_cluster(mapa_shared(smem_u32(bar_a), 0));
                 else mbar_arrive(smem_u32(bar_a));
             }
+            trace_ev(tr && warp == 2, 8, 0);  // epilogue: own part of the query tile stored
         }
-        for (int e = 0; e < kDepth; ++e) {
+        for (int e = 0; e < DEPTH; ++e) {
             ls[e * kQTile + t] = RR_NEG_INF;
             lr[e * kQTile + t] = RR_NO_ROW;
         }
@@ -407,6 +474,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
             mbar_wait(smem_u32(bar_acc_full + acc), acc_phase);
             tc_fence_after();
+            trace_ev(tr && warp == 2, 5, tile);  // epilogue: accumulator complete
             const uint32_t t_acc = lane_addr + a_cols + (uint32_t)(acc * kNT);
             uint32_t r[4][32];
             tmem_ld_x32_nowait(t_acc, r[0]);
@@ -414,6 +482,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tmem_ld_x32_nowait(t_acc + 64, r[2]);
             tmem_ld_x32_nowait(t_acc + 96, r[3]);
             tmem_ld_wait();
+            trace_ev(tr && warp == 2, 6, tile);  // epilogue: tile in registers
             // the registers hold the tile: hand the accumulator back before selecting
             tc_fence_before();
             __syncwarp();
@@ -437,45 +506,70 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             if (!COLLECT && tile == slice && qg < n_active) {
                 // First tile of the launch: the list is empty, so all 128 scores would "survive" and go
                 // through 128 one-by-one inserts while the tensor pipe and the TMA ring wait.  Seed the
-                // list with the two best of each group of 8 columns instead (32 entries, branch-free) and
-                // send only what beats their minimum through the regular path.
-                static_assert(kDepth == 32 && kNT == 128, "seeding fills 2 x 16 groups");
+                // list with the best (DEPTH 32: two best) of each group of 128 / DEPTH * ... columns instead
+                // (branch-free) and send only what beats their minimum through the regular path.
+                static_assert((DEPTH == 32 || DEPTH == 8) && kNT == 128, "seeding fills 2 x 16 or 1 x 8 groups");
                 float mn = __builtin_huge_valf();
                 int mn_e = 0;
+                if (DEPTH == 32) {
 #pragma unroll
-                for (int g = 0; g < 16; ++g) {
-                    float a1 = RR_NEG_INF, a2 = RR_NEG_INF;
-                    int j1 = 0, j2 = 0;
+                    for (int g = 0; g < 16; ++g) {
+                        float a1 = RR_NEG_INF, a2 = RR_NEG_INF;
+                        int j1 = 0, j2 = 0;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float v = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
-                        if (v > a1) {
-                            a2 = a1;
-                            j2 = j1;
-                            a1 = v;
-                            j1 = j;
-                        } else if (v > a2) {
-                            a2 = v;
-                            j2 = j;
+                        for (int j = 0; j < 8; ++j) {
+                            const float v = __uint_as_float(r[g >> 2][(g & 3) * 8 + j]);
+                            if (v > a1) {
+                                a2 = a1;
+                                j2 = j1;
+                                a1 = v;
+                                j1 = j;
+                            } else if (v > a2) {
+                                a2 = v;
+                                j2 = j;
+                            }
                         }
-                    }
-                    ls[(2 * g) * kQTile + t] = a1;
-                    lr[(2 * g) * kQTile + t] = (a1 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j1) : RR_NO_ROW;
-                    ls[(2 * g + 1) * kQTile + t] = a2;
-                    lr[(2 * g + 1) * kQTile + t] = (a2 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j2) : RR_NO_ROW;
-                    if (a1 < mn) {
-                        mn = a1;
-                        mn_e = 2 * g;
-                    }
-                    if (a2 < mn) {
-                        mn = a2;
-                        mn_e = 2 * g + 1;
-                    }
+                        ls[(2 * g) * kQTile + t] = a1;
+                        lr[(2 * g) * kQTile + t] = (a1 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j1) : RR_NO_ROW;
+                        ls[(2 * g + 1) * kQTile + t] = a2;
+                        lr[(2 * g + 1) * kQTile + t] = (a2 > RR_NEG_INF) ? (uint32_t)(row0 + g * 8 + j2) : RR_NO_ROW;
+                        if (a1 < mn) {
+                            mn = a1;
+                            mn_e = 2 * g;
+                        }
+                        if (a2 < mn) {
+                            mn = a2;
+                            mn_e = 2 * g + 1;
+                        }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        if (j == j1 || j == j2) r[g >> 2][(g & 3) * 8 + j] = __float_as_uint(RR_NEG_INF);
+                        for (int j = 0; j < 8; ++j)
+                            if (j == j1 || j == j2) r[g >> 2][(g & 3) * 8 + j] = __float_as_uint(RR_NEG_INF);
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {  // the best of each group of 16 columns
+                        float a1 = RR_NEG_INF;
+                        int j1 = 0;
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float v = __uint_as_float(r[g >> 1][(g & 1) * 16 + j]);
+                            if (v > a1) {
+                                a1 = v;
+                                j1 = j;
+                            }
+                        }
+                        ls[g * kQTile + t] = a1;
+                        lr[g * kQTile + t] = (a1 > RR_NEG_INF) ? (uint32_t)(row0 + g * 16 + j1) : RR_NO_ROW;
+                        if (a1 < mn) {
+                            mn = a1;
+                            mn_e = g;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (j == j1) r[g >> 1][(g & 1) * 16 + j] = __float_as_uint(RR_NEG_INF);
+                    }
                 }
-                thr = mn;  // -inf (and pos = an empty slot) when the tile had fewer than 32 rows
+                thr = mn;  // -inf (and pos = an empty slot) when the tile had fewer than DEPTH rows
                 pos = mn_e;
             }
             // maxima of the 16 groups of 8 columns, then of the tile: hits are sparse (a few
@@ -510,7 +604,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         // a group adds at most 8 entries per thread: drain before the queue could overflow
                         if (__any_sync(RR_FULL, cnt > kPend - 8)) {
                             if (COLLECT) epi_collect(cnt, qg, p, pr, t);
-                            else epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                            else epi_drain<DEPTH>(cnt, thr, pos, ls, lr, ps, pr, t);
                             cnt = 0;
                         }
                     }
@@ -518,24 +612,25 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 // one drain per tile serves every query of the warp that had survivors
                 if (__any_sync(RR_FULL, cnt > 0)) {
                     if (COLLECT) epi_collect(cnt, qg, p, pr, t);
-                    else epi_drain(cnt, thr, pos, ls, lr, ps, pr, t);
+                    else epi_drain<DEPTH>(cnt, thr, pos, ls, lr, ps, pr, t);
                     cnt = 0;
                 }
             }
         }
+        trace_ev(tr && warp == 2, 7, 0);  // epilogue: all tiles selected
         // publish [compact query][list = slice][kDepth]: the list's minimum goes to the LAST slot (the tail
         // that bounds every dropped row; an empty slot there = nothing was dropped), the rest unsorted
         if (!COLLECT && qg < n_active) {
-            const int64_t o = (int64_t)qg * p.cand_stride + (int64_t)slice * kDepth;
+            const int64_t o = (int64_t)qg * p.cand_stride + (int64_t)slice * DEPTH;
             int w = 0;
-            for (int e = 0; e < kDepth; ++e) {
+            for (int e = 0; e < DEPTH; ++e) {
                 if (e == pos) continue;
                 p.cand_s[o + w] = ls[e * kQTile + t];
                 p.cand_r[o + w] = lr[e * kQTile + t];
                 ++w;
             }
-            p.cand_s[o + kDepth - 1] = ls[pos * kQTile + t];
-            p.cand_r[o + kDepth - 1] = lr[pos * kQTile + t];
+            p.cand_s[o + DEPTH - 1] = ls[pos * kQTile + t];
+            p.cand_r[o + DEPTH - 1] = lr[pos * kQTile + t];
         }
     }
 
@@ -547,10 +642,21 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
         if (CG == 2) tmem_dealloc_2cta(tmem_base, kTmemCols);
         else tmem_dealloc(tmem_base, kTmemCols);
     }
+    trace_ev(tr && warp == 0, 9, 0);  // kernel end
     pdl_wait_primary();  // complete only after the previous scan of the chain has
 }
 
 }  // namespace
+
+extern "C" int rr_debug_read_trace(unsigned long long* out, int cap) {
+    unsigned int n = 0;
+    RR_CUDA_CHECK(cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n)));
+    const int m = (int)std::min<unsigned>(n, (unsigned)std::min(cap, kTraceCap));
+    if (m > 0) RR_CUDA_CHECK(cudaMemcpyFromSymbol(out, g_trace, (size_t)m * 16));
+    const unsigned int zero = 0;
+    RR_CUDA_CHECK(cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero)));
+    return m;
+}
 
 bool rr_gemm_scan_supported(const rr_index* h) {
     // the 128-query tile lives in TMEM (up to 768 dims next to one accumulator stage, 512 next to two) and
@@ -560,7 +666,7 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
-template <int CG, bool COLLECT>
+template <int CG, bool COLLECT, int DEPTH>
 static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, bool chain,
                      cudaStream_t stream) {
     const size_t stage_b = (size_t)kStageBytes / CG;
@@ -572,7 +678,7 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     const size_t smem = fixed + (size_t)p.stages * stage_b;
     static std::atomic<bool> attr_done[RR_MAX_DEVICES];  // per (instantiation, device); a double set is harmless
     if (!attr_done[h->device].load(std::memory_order_acquire)) {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
         attr_done[h->device].store(true, std::memory_order_release);
     }
@@ -590,9 +696,16 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = chain ? 2 : 1;
-    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT>, tx, tq, p));
+    cfg.numAttrs = rr_pdl_enabled() ? 2 : 1;
+    p.chained = (chain && rr_pdl_enabled()) ? 1 : 0;
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT, DEPTH>, tx, tq, p));
     return RR_OK;
+}
+
+int rr_gemm_scan_list_depth(const rr_index* h) {
+    // small shards: short lists (see rr_gemm_scan_kernel); "gemm_depth" (testing knob) forces 8 or 32
+    if (h->gemm_depth == 8 || h->gemm_depth == 32) return h->gemm_depth;
+    return (h->n <= (int64_t)h->sm_count * 16384 && h->n >= 64 * (int64_t)kNT) ? 8 : kDepth;
 }
 
 static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
@@ -670,6 +783,8 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     p.cand_stride = cand_stride;
     p.min_active = min_active;
     p.max_active = max_active;
+    static const int trace_on = getenv("RR_TRACE") != nullptr;
+    p.trace = trace_on;
     p.theta = collect ? collect->theta : nullptr;
     p.col_rows = collect ? collect->rows : nullptr;
     p.col_cnt = collect ? collect->cnt : nullptr;
@@ -683,8 +798,11 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     int rc = rr_make_tmap_bf16_rows(&tq, qbf16_dev, nq_rows, h->d_pad, kQTile);
     if (rc != RR_OK) return rc;
     if (collect)
-        return cta_group == 2 ? launch_cg<2, true>(h, h->tmap_hi64, tq, p, chain, stream)
-                              : launch_cg<1, true>(h, h->tmap_hi, tq, p, chain, stream);
-    return cta_group == 2 ? launch_cg<2, false>(h, h->tmap_hi64, tq, p, chain, stream)
-                          : launch_cg<1, false>(h, h->tmap_hi, tq, p, chain, stream);
+        return cta_group == 2 ? launch_cg<2, true, kDepth>(h, h->tmap_hi64, tq, p, chain, stream)
+                              : launch_cg<1, true, kDepth>(h, h->tmap_hi, tq, p, chain, stream);
+    if (rr_gemm_scan_list_depth(h) == 8)
+        return cta_group == 2 ? launch_cg<2, false, 8>(h, h->tmap_hi64, tq, p, chain, stream)
+                              : launch_cg<1, false, 8>(h, h->tmap_hi, tq, p, chain, stream);
+    return cta_group == 2 ? launch_cg<2, false, kDepth>(h, h->tmap_hi64, tq, p, chain, stream)
+                          : launch_cg<1, false, kDepth>(h, h->tmap_hi, tq, p, chain, stream);
 }

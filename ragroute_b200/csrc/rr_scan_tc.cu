@@ -44,6 +44,7 @@ struct TcParams {
     int nq_tile;  // valid queries in this pass (<= QT)
     int q_row0;   // first row of the pass inside the query buffer
     int stages;
+    int chained;  // 1: directly follows another scan of the same step (see the PDL notes in rr_tc_scan_kernel)
     const uint8_t* active;   // [nq_tile]
     const int* any_active;   // device flag: 0 -> nothing routed here, exit at once
     rr_scan_counters* counters;  // profiling: bytes streamed / flops scored by passes that really ran (or NULL)
@@ -93,6 +94,12 @@ template <int QT>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_tc_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                   const TcParams p) {
+    // Programmatic dependent launch.  The scans of one step touch disjoint memory, so a CHAINED scan starts at
+    // once (its predecessor scan has already waited for everything before the chain) and lets its successor
+    // start too; the FIRST scan of a chain waits here for the kernels before it (query preparation) and only
+    // then releases its successor.  Every scan waits again before it exits, so it completes after its
+    // predecessor and whatever follows the chain sees all of it done.
+    if (!p.chained) pdl_wait_primary();
     pdl_launch_dependents();  // the next scan of the step may take SMs as they free up
     if (*p.any_active == 0) {  // no query routed to this source: do not touch the corpus
         pdl_wait_primary();
@@ -349,7 +356,8 @@ int launch_qt(rr_index* h, const CUtensorMap& tq, const TcParams& p, int grid, s
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = chain ? 1 : 0;
+    cfg.numAttrs = rr_pdl_enabled() ? 1 : 0;
+    (void)chain;
     RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_tc_scan_kernel<QT>, h->tmap_hi, tq, p));
     return RR_OK;
 }
@@ -390,6 +398,7 @@ int rr_tc_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int64_t q_rows_tot
     p.nq_tile = nq_tile;
     p.q_row0 = q_row0;
     p.stages = pl.stages;
+    p.chained = (chain && rr_pdl_enabled()) ? 1 : 0;
     p.active = active_dev;
     p.any_active = any_active_dev;
     p.counters = counters_dev;

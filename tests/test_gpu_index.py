@@ -353,6 +353,22 @@ def test_gemm_path_wide_rows_up_to_1024_dims(faiss, d):
         assert np.array_equal(I, Ie) and np.array_equal(D, De)
 
 
+@pytest.mark.parametrize("depth", [8, 32])
+@pytest.mark.parametrize("nq,path", [(40, 2), (128, 2), (300, 3), (1100, 0)])
+def test_gemm_path_list_depths_agree_with_exact(faiss, depth, nq, path):
+    """Both candidate-list depths of the queries-in-TMEM scan (8 for small shards, 32 for large ones; forced here)
+    on a MedRAG-shaped corpus: no certificate failure and bit-identical to the exact mode."""
+    d, k = 768, 32
+    xb = syn.corpus_rows(1, 50000, d)
+    q = syn.queries(nq, d, [1], seed=nq + depth)
+    ix = _gemm_index(faiss, xb, path)
+    ix.set_param("gemm_depth", depth)
+    D, I = ix.search(q, k)
+    assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data (depth {depth}): {ix.stats()}"
+    De, Ie = _index(faiss, xb, "exact").search(q, k)
+    assert np.array_equal(I, Ie) and np.array_equal(D, De)
+
+
 def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
     """On benign MedRAG-shaped data the certificate must pass for every query (otherwise
     the exact rescan would hide a broken tensor-core kernel), for 1, 2 and 8 query tiles."""

@@ -79,6 +79,21 @@ def test_router_batch_sizes_and_errors(cuda_required):
         FusedCorpusRouter(10).load_state_dict({})
 
 
+def test_router_logits_do_not_depend_on_the_batch(cuda_required):
+    """fc1 is summed in one fixed tree whether a cluster of CTAs (small batches) or single CTAs (large ones)
+    compute it: a query's logits and mask are bit-identical alone, in a batch of 100 and in a batch of 300."""
+    c = RouterCase("medrag")
+    r = _make_router(c)
+    rng = np.random.default_rng(4)
+    q = torch.from_numpy(rng.uniform(-0.4, 0.4, size=(300, c.d_max)).astype(np.float32)).cuda()
+    m300, l300 = r.select(q, c.threshold, return_logits=True)
+    m100, l100 = r.select(q[:100].contiguous(), c.threshold, return_logits=True)
+    assert torch.equal(l300[:100], l100) and torch.equal(m300[:100], m100)
+    for b in (0, 57, 99):
+        m1, l1 = r.select(q[b:b + 1].contiguous(), c.threshold, return_logits=True)
+        assert torch.equal(l1[0], l300[b]) and torch.equal(m1[0], m300[b])
+
+
 def test_rerank_matches_reference_golden(cuda_required):
     from ragroute_b200 import rerank
     g = np.load(os.path.join(GOLDEN, "rerank.npz"))
