@@ -79,6 +79,10 @@ int64_t rr_index_ntotal(const rr_index_t* h);
 int rr_index_dim(const rr_index_t* h);
 /* index.reconstruct_n(row0, n): exact fp32 rows back out of the stored planes */
 int rr_index_reconstruct(rr_index_t* h, int64_t row0, int64_t n, float* out_dev, void* stream);
+/* Column mean of the stored rows (fp64 sums over the exact fp32 values, rounded once): the per-source
+ * centroid the router reads from <corpus>_stats.json["centroid"] (router.py:136-151; the reference computes
+ * it offline).  out_host [d] fp32; synchronous. */
+int rr_index_centroid(rr_index_t* h, float* out_host);
 /* ids returned by search are local row numbers + offset (row-sharded corpora) */
 int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
 /* "mode" (RR_MODE_*), "kprime" (candidates rescored per query, default 128),

@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rr_index_ntotal": (c_int64, [c_void_p]),
     "rr_index_dim": (c_int, [c_void_p]),
     "rr_index_reconstruct": (c_int, [c_void_p, c_int64, c_int64, _P, _P]),
+    "rr_index_centroid": (c_int, [c_void_p, _P]),
     "rr_index_set_id_offset": (c_int, [c_void_p, c_int64]),
     "rr_index_set_param": (c_int, [c_void_p, c_char_p, c_double]),
     "rr_index_search": (c_int, [c_void_p, _P, c_int64, c_int, _P, _P, _P]),

@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <atomic>
 #include <new>
+#include <vector>
 
 #include "rr_index_internal.cuh"
 #include "rr_topm.cuh"
@@ -114,6 +115,25 @@ rr_normalize_l2_kernel(float* __restrict__ x, int64_t n, int d) {
     if (tot > 0.f) {
         const float inv = 1.0f / sqrtf(tot);
         for (int e = threadIdx.x; e < d; e += blockDim.x) xr[e] *= inv;
+    }
+}
+
+// Column sums of the stored rows in fp64 (the router's per-source centroid, router.py:136-151 reads it from
+// <corpus>_stats.json["centroid"]): block b sums rows b, b + gridDim.x, ...; thread t the columns t, t + 256, ...
+__global__ void __launch_bounds__(256)
+rr_column_sums_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t n, int d, int d_pad,
+                      double* __restrict__ sums) {
+    for (int e0 = threadIdx.x * 2; e0 < d; e0 += 512) {
+        double a0 = 0.0, a1 = 0.0;
+        for (int64_t row = blockIdx.x; row < n; row += gridDim.x) {
+            const uint32_t hw = *reinterpret_cast<const uint32_t*>(hi + row * d_pad + e0);
+            const uint32_t lw = *reinterpret_cast<const uint32_t*>(lo + row * d_pad + e0);
+            const float2 v = rr_join_f32x2(hw, lw);
+            a0 += (double)v.x;
+            a1 += (double)v.y;
+        }
+        atomicAdd(sums + e0, a0);
+        if (e0 + 1 < d) atomicAdd(sums + e0 + 1, a1);
     }
 }
 
@@ -257,7 +277,7 @@ rr_prep_queries_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
 // begin + prep in ONE launch for chunks of <= RR_FUSED_PREP_MAX padded queries (every small-batch step: the two
 // launches cost more than their work).  One block of 1024 threads per source: zero the control block, compact the
 // routed queries (large-batch path), then one WARP per query converts it (same arithmetic as the kernel above).
-constexpr int RR_FUSED_PREP_MAX = 256;
+constexpr int RR_FUSED_PREP_MAX = 64;  // padded queries: beyond one or two queries per warp the grid-wide kernels win
 
 __global__ void __launch_bounds__(1024)
 rr_begin_prep_fused_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
@@ -291,28 +311,61 @@ rr_begin_prep_fused_kernel(const __grid_constant__ rr_multi<rr_prep_args> m) {
     }
     if (tid == 0) s_any = 0;
     __syncthreads();
+    const bool vec4 = (d & 3) == 0 && (reinterpret_cast<uintptr_t>(a.q) & 15) == 0;
     for (int b = w; b < nq_pad; b += 32) {
         uint16_t* out = a.qbf16 + (int64_t)((a.compact && b < nq) ? s_cpos[b] : b) * d_pad;
         if (b >= nq) {
-            for (int e = lane; e < d_pad; e += 32) out[e] = 0;
+            for (int e = lane * 8; e < d_pad; e += 256) *reinterpret_cast<uint4*>(out + e) = make_uint4(0, 0, 0, 0);
             if (lane == 0) a.active[b] = 0;
             continue;
         }
         const bool act = mask ? (mask[(int64_t)b * a.mask_stride] != 0) : true;
         const float* qr = a.q + (int64_t)b * d;
         double hs = 0.0, es = 0.0;
-        for (int e = lane; e < d_pad; e += 32) {
-            uint16_t h = 0, l = 0;
-            if (e < d && act) {
-                const float v = qr[e];
-                rr_split_f32(v, h, l);
-                const float vh = __uint_as_float((uint32_t)h << 16);
-                const float dv = v - vh;
-                hs = fma((double)vh, (double)vh, hs);
-                es = fma((double)dv, (double)dv, es);
+        if (vec4) {
+            // 8 independent 16-byte loads in flight per lane (1024 dimensions per round): the row is one latency
+            for (int e0 = 0; e0 < d_pad; e0 += 1024) {
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + (lane + 32 * u) * 4;
+                    v[u] = (e < d && act) ? __ldg(reinterpret_cast<const float4*>(qr + e)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = e0 + (lane + 32 * u) * 4;
+                    if (e < d_pad) {
+                        const float x4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+                        uint16_t h4[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint16_t l;
+                            rr_split_f32(x4[c], h4[c], l);
+                            (void)l;
+                            const float vh = __uint_as_float((uint32_t)h4[c] << 16);
+                            const float dv = x4[c] - vh;
+                            hs = fma((double)vh, (double)vh, hs);
+                            es = fma((double)dv, (double)dv, es);
+                        }
+                        *reinterpret_cast<uint2*>(out + e) =
+                            make_uint2((uint32_t)h4[0] | ((uint32_t)h4[1] << 16), (uint32_t)h4[2] | ((uint32_t)h4[3] << 16));
+                    }
+                }
             }
-            (void)l;
-            out[e] = h;
+        } else {
+            for (int e = lane; e < d_pad; e += 32) {
+                uint16_t h = 0, l = 0;
+                if (e < d && act) {
+                    const float v = qr[e];
+                    rr_split_f32(v, h, l);
+                    const float vh = __uint_as_float((uint32_t)h << 16);
+                    const float dv = v - vh;
+                    hs = fma((double)vh, (double)vh, hs);
+                    es = fma((double)dv, (double)dv, es);
+                }
+                (void)l;
+                out[e] = h;
+            }
         }
         hs = rr_warp_sum(hs);
         es = rr_warp_sum(es);
@@ -723,17 +776,29 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
             need -= cgt;
             lo = wlo;
             hi = whi;
-            if (n_above + ceq <= RR_FIN_MAXSEL) {  // the whole boundary bin fits
-                take_eq = ceq;
-                break;
-            }
-            if (sh == 0) {  // one key value, more copies than fit: equal keys, any `need` of them will do
-                take_eq = need;
-                break;
+            if (RESCORE) {
+                // Exactly kp candidates are rescored (a power of two keeps the sort small): `need` members of the
+                // boundary bin, whichever arrive first.  Any choice is sound -- t_rest below is the best key really
+                // left behind -- and a crowded bin is only refined while that would tighten t_rest noticeably.
+                if (ceq - need <= 8 || sh == 0) {
+                    take_eq = need;
+                    break;
+                }
+            } else {
+                if (n_above + ceq <= RR_FIN_MAXSEL) {  // the whole boundary bin fits: the exact order is sorted out below
+                    take_eq = ceq;
+                    break;
+                }
+                if (sh == 0) {  // (keys carry the row: they are unique, a single key value never overflows)
+                    take_eq = need;
+                    break;
+                }
             }
             __syncthreads();  // s_bstar / hist are rewritten by the next level
         }
-        // gather: keys above the window all go in, the window's keys fill the remaining slots
+        // gather: keys above the window all go in, the window's keys fill the remaining slots; the best key
+        // left behind bounds every unselected candidate (t_rest)
+        unsigned long long rest = 0ull;
         for (int i = tid; i < n_cand; i += n_threads) {
             const uint32_t r = cr[i];
             if (r == RR_NO_ROW) continue;
@@ -748,15 +813,23 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
                 if (p < take_eq) {
                     sel_s[n_above + p] = sc;
                     sel_r[n_above + p] = r;
+                } else {
+                    rest = max(rest, key);
                 }
+            } else {
+                rest = max(rest, key);
             }
         }
-        kp = n_above + take_eq;  // what was selected: >= the kp asked for
-        if (n_valid > kp) {
-            // every unselected candidate's key is below the window (or, when equal keys were cut, inside it)
-            const unsigned long long edge = (take_eq < (int)s_ceq) ? lo : (lo > 0 ? lo - 1 : 0);
-            const uint32_t e32 = (uint32_t)(RESCORE ? edge : (edge >> 32));
-            t_rest = e32 ? rr_key_float(e32) : RR_NEG_INF;
+        kp = n_above + take_eq;  // what was selected (exact finalize: possibly more than the k asked for)
+        if (RESCORE && n_valid > kp) {  // (uniform: both from shared memory)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rest = max(rest, __shfl_xor_sync(RR_FULL, rest, o));
+            __syncthreads();  // s_kmax was read by everyone long ago: reuse it
+            if (lane == 0) s_kmax[w] = rest;
+            __syncthreads();
+            rest = s_kmax[0];
+            for (int i = 1; i < (n_threads >> 5); ++i) rest = max(rest, s_kmax[i]);
+            t_rest = rest ? rr_key_float((uint32_t)rest) : RR_NEG_INF;
         }
     }
     // pad the selection to a power of two for the sort
@@ -1283,6 +1356,30 @@ extern "C" int rr_index_reconstruct(rr_index_t* h, int64_t row0, int64_t n, floa
     return RR_OK;
 }
 
+extern "C" int rr_index_centroid(rr_index_t* h, float* out_host) {
+    RR_REQUIRE(h != nullptr && out_host != nullptr, "rr_index_centroid: NULL argument");
+    RR_REQUIRE(h->n > 0, "rr_index_centroid: empty index");
+    rr_device_guard g(h->device);
+    double* sums = nullptr;
+    RR_CUDA_CHECK(cudaDeviceSynchronize());  // rows added asynchronously on any stream are in place
+    RR_CUDA_CHECK(cudaMalloc(&sums, (size_t)h->d * sizeof(double)));
+    cudaError_t e = cudaMemset(sums, 0, (size_t)h->d * sizeof(double));
+    if (e == cudaSuccess) {
+        const int blocks = (int)std::min<int64_t>(h->n, (int64_t)h->sm_count * 16);
+        rr_column_sums_kernel<<<blocks, 256>>>(h->hi, h->lo, h->n, h->d, h->d_pad, sums);
+        e = cudaGetLastError();
+    }
+    std::vector<double> host((size_t)h->d);
+    if (e == cudaSuccess) e = cudaMemcpy(host.data(), sums, (size_t)h->d * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(sums);
+    if (e != cudaSuccess) {
+        rr_set_error("rr_index_centroid: %s", cudaGetErrorString(e));
+        return RR_ERR_CUDA;
+    }
+    for (int i = 0; i < h->d; ++i) out_host[i] = (float)(host[(size_t)i] / (double)h->n);
+    return RR_OK;
+}
+
 extern "C" int rr_index_set_id_offset(rr_index_t* h, int64_t offset) {
     RR_REQUIRE(h != nullptr, "rr_index_set_id_offset: NULL handle");
     h->id_offset = offset;
@@ -1644,7 +1741,7 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
             a.n_lists = 0;
             a.lists_from_ctl = 1;
             a.cpos = p.cpos;
-            a.depth = rr_gemm_scan_list_depth(h);
+            a.depth = rr_gemm_scan_list_depth(h, nq);
         } else if (p.use_tc) {
             for (int p0 = 0; p0 < nq; p0 += p.qt) {
                 const int nqt = std::min(p.qt, nq - p0);

@@ -122,7 +122,7 @@ int rr_make_tmap_bf16_rows(CUtensorMap* out, const void* ptr, int64_t rows, int 
 // the number of slices in ctl->n_lists.
 bool rr_gemm_scan_supported(const rr_index* h);
 int rr_gemm_scan_max_lists(const rr_index* h);
-int rr_gemm_scan_list_depth(const rr_index* h);  // entries per (corpus slice, query) list for this index: 8 or 32
+int rr_gemm_scan_list_depth(const rr_index* h, int nq);  // entries per (corpus slice, query) list of a chunk of nq queries: 8 or 32
 // cta_group: 1 = one CTA per 128-query tile; 2 = CTA pairs (cluster of 2, 256 queries per pair),
 // for which qbf16 holds ceil(nq / 256) * 256 rows.
 int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,

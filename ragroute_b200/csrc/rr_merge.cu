@@ -9,10 +9,12 @@
 #include <algorithm>
 
 #include "rr_common.cuh"
+#include "rr_topm.cuh"
 
 namespace {
 constexpr int kWarpsPerBlock = 4;
 constexpr uint32_t kDead = 0xFFFFFFFFu;  // key slot of an empty / already taken entry
+constexpr int kSortMaxL = 256;           // up to this many entries per query: one register sort
 
 // Input = n_seg segments of [B, seg_len] lists (one segment per rank after the all-gather; one segment
 // for a plain merge); entry (seg, j) of query b has input position seg * seg_len + j.
@@ -71,7 +73,72 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(cons
     const int64_t b = (int64_t)blockIdx.x * kWarpsPerBlock + w;
     if (b >= a.B) return;
     const int L = a.n_seg * a.seg_len, k = a.k;
-    uint32_t* keys = keys_all + (size_t)w * (L + k);
+    const int L_pad = L <= 32 ? 32 : L <= 64 ? 64 : L <= 128 ? 128 : 256;   // (fast path only: L <= 256)
+    uint32_t* keys = keys_all + (size_t)w * max(L + k, L <= kSortMaxL ? 2 * L_pad : 0);
+    const float pad = a.descending ? -3.402823466e+38f : 3.402823466e+38f;
+    if (L <= kSortMaxL) {
+        // Fast path for the reference's shapes (L = S * k <= 256): ONE register bitonic sort of the (score,
+        // position) pairs instead of k dependent select rounds (32 rounds of redux + rescan were 2/3 of the
+        // kernel's 11 us).  It orders equal scores by position -- the rule of the plain merge; lists with
+        // source structure order them by (source, id, position), so a query whose first k+1 sorted entries
+        // contain equal scores (duplicated documents: rare) falls through to the select rounds below.
+        float* ks = reinterpret_cast<float*>(keys);
+        uint32_t* kr = keys + L_pad;
+        int nv = 0;
+        for (int i = lane; i < L_pad; i += 32) {
+            float sv = RR_NEG_INF;
+            uint32_t pos = 0xFFFFFFFFu;
+            if (i < L) {
+                const int seg = i / a.seg_len, j = i - seg * a.seg_len;
+                const float v = a.s[seg * a.seg_stride_s + b * a.seg_len + j];
+                const int64_t idv = a.id[seg * a.seg_stride_id + b * a.seg_len + j];
+                if (idv >= 0 && v == v) {
+                    sv = a.descending ? v : -v;
+                    pos = (uint32_t)i;
+                    ++nv;
+                }
+            }
+            ks[i] = sv;
+            kr[i] = pos;
+        }
+        nv = __reduce_add_sync(RR_FULL, nv);
+        __syncwarp();
+        switch (L_pad >> 5) {
+            case 1: rr_warp_sort_smem<1>(ks, kr, lane); break;
+            case 2: rr_warp_sort_smem<2>(ks, kr, lane); break;
+            case 4: rr_warp_sort_smem<4>(ks, kr, lane); break;
+            default: rr_warp_sort_smem<8>(ks, kr, lane); break;
+        }
+        __syncwarp();
+        const int n_out = min(k, nv);
+        bool tie = false;
+        if (a.list_len > 0)
+            for (int r = lane; r < n_out; r += 32) tie |= (r + 1 < nv) && ks[r] == ks[r + 1];
+        if (!__any_sync(RR_FULL, tie)) {
+            for (int r = lane; r < k; r += 32) {
+                float sv = pad;
+                int64_t iv = -1;
+                int pos = -1, src = -1, rank = -1;
+                if (r < n_out) {
+                    pos = (int)kr[r];
+                    const int seg = pos / a.seg_len, j = pos - seg * a.seg_len;
+                    sv = a.s[seg * a.seg_stride_s + b * a.seg_len + j];
+                    iv = a.id[seg * a.seg_stride_id + b * a.seg_len + j];
+                    if (a.list_len > 0) {
+                        rank = seg;
+                        src = j / a.list_len;
+                    }
+                }
+                a.os[b * k + r] = sv;
+                a.oid[b * k + r] = iv;
+                if (a.opos) a.opos[b * k + r] = pos;
+                if (a.osrc) a.osrc[b * k + r] = src;
+                if (a.orank) a.orank[b * k + r] = rank;
+            }
+            return;
+        }
+        __syncwarp();  // equal scores near the top: the select rounds below apply the full tie order
+    }
     int* wins = reinterpret_cast<int*>(keys + L);  // winner of every round
     for (int i = lane; i < L; i += 32) {
         const int seg = i / a.seg_len, j = i - seg * a.seg_len;
@@ -112,7 +179,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(cons
     }
     __syncwarp();
     // write the winners out in parallel; pad the rest like faiss / the oracle
-    const float pad = a.descending ? -3.402823466e+38f : 3.402823466e+38f;
     for (int r = lane; r < k; r += 32) {
         float sv = pad;
         int64_t iv = -1;
@@ -137,7 +203,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) rr_merge_topk_kernel(cons
 
 int merge_launch(const MergeArgs& a, cudaStream_t stream) {
     const int L = a.n_seg * a.seg_len;
-    const size_t smem = (size_t)kWarpsPerBlock * (L + a.k) * sizeof(uint32_t);
+    const int L_pad = L <= 32 ? 32 : L <= 64 ? 64 : L <= 128 ? 128 : 256;
+    const size_t smem = (size_t)kWarpsPerBlock * std::max(L + a.k, L <= kSortMaxL ? 2 * L_pad : 0) * sizeof(uint32_t);
     if (smem > (48u << 10)) {
         RR_CUDA_CHECK(cudaFuncSetAttribute(rr_merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)smem));

@@ -461,6 +461,8 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             }
             trace_ev(tr && warp == 2, 8, 0);  // epilogue: own part of the query tile stored
         }
+        // the transposing stage of ALL four warps aliases the list arrays initialised next: wait for the slowest
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         for (int e = 0; e < DEPTH; ++e) {
             ls[e * kQTile + t] = RR_NEG_INF;
             lr[e * kQTile + t] = RR_NO_ROW;
@@ -702,10 +704,14 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     return RR_OK;
 }
 
-int rr_gemm_scan_list_depth(const rr_index* h) {
-    // small shards: short lists (see rr_gemm_scan_kernel); "gemm_depth" (testing knob) forces 8 or 32
+int rr_gemm_scan_list_depth(const rr_index* h, int nq) {
+    // Short lists for small shards (see rr_gemm_scan_kernel) -- but only when the chunk is ONE query tile (<= 128
+    // queries on single CTAs, <= 256 on pairs), so that every query gets a list from each of the 148 / 74 corpus
+    // slices: with t query tiles the slices (and lists per query) shrink t-fold and 8-entry lists no longer hold
+    // the k' = 128 candidates the finalize wants.  "gemm_depth" (testing knob) forces 8 or 32.
     if (h->gemm_depth == 8 || h->gemm_depth == 32) return h->gemm_depth;
-    return (h->n <= (int64_t)h->sm_count * 16384 && h->n >= 64 * (int64_t)kNT) ? 8 : kDepth;
+    const bool small_shard = h->n <= (int64_t)h->sm_count * 16384 && h->n >= 64 * (int64_t)kNT;
+    return (small_shard && nq <= 2 * kQTile) ? 8 : kDepth;
 }
 
 static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_group, rr_chunk_ctl* ctl_dev,
@@ -800,7 +806,7 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     if (collect)
         return cta_group == 2 ? launch_cg<2, true, kDepth>(h, h->tmap_hi64, tq, p, chain, stream)
                               : launch_cg<1, true, kDepth>(h, h->tmap_hi, tq, p, chain, stream);
-    if (rr_gemm_scan_list_depth(h) == 8)
+    if (rr_gemm_scan_list_depth(h, nq) == 8)
         return cta_group == 2 ? launch_cg<2, false, 8>(h, h->tmap_hi64, tq, p, chain, stream)
                               : launch_cg<1, false, 8>(h, h->tmap_hi, tq, p, chain, stream);
     return cta_group == 2 ? launch_cg<2, false, kDepth>(h, h->tmap_hi64, tq, p, chain, stream)

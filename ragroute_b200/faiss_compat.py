@@ -108,6 +108,12 @@ class IndexFlatIP:
         n = self.ntotal - i0 if n < 0 else n
         return self.reconstruct_tensor(i0, n).cpu().numpy()
 
+    def centroid(self) -> np.ndarray:
+        """Column mean of the stored rows, fp32 [d] (what the router's <corpus>_stats.json holds, router.py:136-151)."""
+        out = np.empty(self.d, dtype=np.float32)
+        _lib.check(self._lib.rr_index_centroid(self._h, out.ctypes.data))
+        return out
+
     def reconstruct(self, i: int) -> np.ndarray:
         return self.reconstruct_n(i, 1)[0]
 
