@@ -34,6 +34,7 @@ import os
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 import argparse  # noqa: E402
+import datetime  # noqa: E402
 import gc  # noqa: E402
 import json  # noqa: E402
 import sys  # noqa: E402
@@ -521,7 +522,8 @@ def gpu_main(args, spec: Spec):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # a collective that does not complete is a bug here, never a slow step: fail in minutes, not in ten
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     if world != args.gpus and rank == 0:
         log(f"[bench] note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
     lib = _lib.load()
@@ -745,13 +747,10 @@ def gpu_main(args, spec: Spec):
             if b == 64:
                 roofline_small = rf
 
-    mask_density = None
-    if rank == 0:
-        try:
-            qd = w.to_device(w.pinned_queries(B, 42))
-            mask_density = float(w.step_dev(qd)["mask"].float().mean().item())
-        except Exception:  # noqa: BLE001
-            pass
+    # (every rank runs this step: a search is a collective when the federation is sharded)
+    qd = w.to_device(w.pinned_queries(B, 42))
+    mask_density = float(w.step_dev(qd)["mask"].float().mean().item())
+    del qd
     local_rows = w.local_rows
 
     # near-duplicate corpus leg: the same workload with documents stored as runs of

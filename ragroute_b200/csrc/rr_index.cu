@@ -720,9 +720,19 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
     // does not fit (exact ties) is cut by position.  One pass in the common case -- the 4 (8) passes of an
     // 8-bit radix select with their 12 (24) block barriers were a third of this kernel.
     float t_rest = RR_NEG_INF;
+    // |bf16 score - exact score| <= eps0 for every row of the corpus (derivation at the certificate below)
+    double eps0 = 0.0;
+    if (RESCORE) {
+        const double xn = (double)__uint_as_float(a.max_norm_bits[0]);
+        const double dxn = (double)__uint_as_float(a.max_norm_bits[1]);
+        const double qhn = (double)a.qnorm[qi];
+        const double dqn = (double)a.qnorm[a.nq_pad + qi];
+        eps0 = (qhn * dxn + dqn * xn + (double)a.d_pad * 2.384185791015625e-7 * qhn * (xn + dxn)) * 1.00001 + 1e-30;
+    }
     if (kp > 0) {
         unsigned long long lo = kmin, hi = kmax;
         int need = kp, n_above = 0, take_eq = 0;
+        bool first = true;
         const int per = RR_FIN_BINS / n_threads;  // bins per thread in the suffix scan (4 or 8)
         for (;;) {
             const unsigned long long range = hi - lo;
@@ -756,6 +766,39 @@ __device__ __forceinline__ void rr_finalize_one(const rr_finalize_args& a, const
             for (int i = 0; i < w; ++i) before += s_scan[i];
             incl += before;
             const uint32_t excl = incl - tot;
+            if (RESCORE && first && kp > a.k) {
+                // How many candidates are worth rescoring?  With c_k = the k-th best bf16 score, k rows have exact
+                // score >= c_k - eps0, so a candidate whose bf16 score is below c_k - 2 eps0 has exact score
+                // < c_k - eps0 <= the true k-th score: it cannot be in the top-k.  Only the candidates at or
+                // above that line are rescored (at most kprime, at least k) -- typically half of kprime, and
+                // the rescoring gathers are the bulk of this kernel.  (Bins make both edges conservative.)
+                if (excl < (uint32_t)a.k && (uint32_t)a.k <= incl) {
+                    uint32_t run = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j < per && run < (uint32_t)a.k && (uint32_t)a.k <= run + c[j]) s_bstar = RR_FIN_BINS - 1 - (tid * per + j);
+                        run += c[j];
+                    }
+                }
+                __syncthreads();
+                const float c_k_lo = rr_key_float((uint32_t)(lo + ((unsigned long long)s_bstar << sh)));  // <= c_k
+                const float line = __double2float_rd((double)c_k_lo - 2.0 * eps0 - fabs((double)c_k_lo) * 2.4e-7);
+                const unsigned long long line_key = rr_float_key(line);
+                const int bt = line_key <= lo ? 0 : (int)min((line_key - lo) >> sh, (unsigned long long)(RR_FIN_BINS - 1));
+                const int jt = RR_FIN_BINS - 1 - bt - tid * per;  // position of bin bt among this thread's bins
+                if (jt >= 0 && jt < per) {
+                    uint32_t run = excl;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j <= jt) run += c[j];
+                    s_cgt = (int)run;  // candidates in the bins at or above the line
+                }
+                __syncthreads();
+                need = min(kp, max(a.k, s_cgt));
+                kp = need;
+                __syncthreads();  // s_bstar / s_cgt are written again right below
+            }
+            first = false;
             if (excl < (uint32_t)need && (uint32_t)need <= incl) {  // exactly one thread
                 uint32_t run = excl;
 #pragma unroll

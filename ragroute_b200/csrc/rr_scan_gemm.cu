@@ -87,11 +87,13 @@ struct GemmParams {
     int64_t cand_stride;
 };
 
-// Timeline tracing (debugging aid, RR_TRACE=1 in the environment): block 0 records (tag, tile, globaltimer) events
-// of its three roles into a device array that rr_debug_read_trace copies out.  Off: one predictable branch.
+// Timeline tracing (debugging aid): a library built with -DRR_TRACE_BUILD (RR_BUILD_TRACE=1 for
+// __graft_entry__.build_cuda) and run with RR_TRACE=1 has block 0 record (tag, tile, globaltimer) events of its
+// three roles into a device array that rr_debug_read_trace copies out.
 constexpr int kTraceCap = 4096;
 __device__ unsigned long long g_trace[kTraceCap * 2];
 __device__ unsigned int g_trace_n;
+#ifdef RR_TRACE_BUILD
 __device__ __forceinline__ void trace_ev(int on, int tag, int tile) {
     if (!on) return;
     unsigned long long t;
@@ -102,6 +104,11 @@ __device__ __forceinline__ void trace_ev(int on, int tag, int tile) {
         g_trace[2 * i + 1] = t;
     }
 }
+#else
+// (compiled out of the product build: a lane-dependent branch in the MMA issuer's converged loop takes its
+// descriptors out of the uniform registers -- measured ~10 % of the tensor rate at batch 2048)
+#define trace_ev(on, tag, tile) ((void)0)
+#endif
 
 // Per-thread state: unsorted top-kDepth list of the thread's query in shared memory, entry e of
 // thread t at [e * kQTile + t] (conflict-free across a warp); `thr` = the list's minimum score
@@ -242,7 +249,9 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+#ifdef RR_TRACE_BUILD
     const int tr = (p.trace && blockIdx.x == 0 && lane == 0) ? 1 : 0;
+#endif
     trace_ev(tr && warp == 0, 0, 0);  // kernel start
 
     // Barrier protocol for a pair (CG = 2): the LEADER owns bar_full (armed by its producer with the

@@ -54,7 +54,8 @@ def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import datetime
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=120))
     rows = {"pubmed": 239_001, "statpearls": 30_100, "textbooks": 12_500, "wikipedia": 299_003}
     sharded, local_rows = build_medrag_federation(rows, rank=rank, world=world, device=local)
     whole, _ = build_medrag_federation(rows, rank=0, world=1, device=local)
