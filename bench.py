@@ -645,10 +645,17 @@ def gpu_main(args, spec: Spec):
         from ragroute_b200.collector import MicroBatcher
         loop = asyncio.new_event_loop()
 
+        pinned = {}  # per encoder slot: one pinned staging buffer [batch, d], reused by every wave
+
         def batch_fn(items):
             # items: per request the tuple of per-encoder embeddings [1, d] (host) -> one pinned batch per encoder
             cols = list(zip(*items))
-            qh = [torch.cat(c, dim=0).pin_memory() for c in cols]
+            qh = []
+            for e, c in enumerate(cols):
+                buf = pinned.get(e)
+                if buf is None:
+                    buf = pinned[e] = torch.empty((batch, c[0].shape[1]), dtype=torch.float32).pin_memory()
+                qh.append(torch.cat(c, dim=0, out=buf[:len(c)]))
             s, i, src = w.step_host(qh if w.multi else qh[0])
             return [(s[b], i[b], src[b]) for b in range(len(items))]
 

@@ -1940,6 +1940,30 @@ static int rr_run_chunk(rr_chunk_plan* plans, int S, int nq, int k, cudaStream_t
     return RR_OK;
 }
 
+// Sources that hold no rows on this device (whole-source placement: a rank passes an empty index for the corpora
+// that live elsewhere) answer with padding rows -- one launch for all of them instead of a pipeline each.
+struct rr_pad_args {
+    float* D;
+    int64_t* I;
+    int64_t nq;
+    int64_t out_stride;
+    int k;
+    int n_sources;
+    unsigned long long empty[4];  // bit s: source s is empty
+};
+__global__ void __launch_bounds__(256) rr_fill_padding_kernel(const rr_pad_args a) {
+    rr_pdl_enter();
+    const int cols = a.n_sources * a.k;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.nq * cols; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = i / cols;
+        const int c = (int)(i - b * cols), s = c / a.k;
+        if ((a.empty[s >> 6] >> (s & 63)) & 1ull) {
+            a.D[b * a.out_stride + c] = -3.402823466e+38f;
+            a.I[b * a.out_stride + c] = -1;
+        }
+    }
+}
+
 static int64_t rr_chunk_size(const rr_index* h, int64_t nq) {
     return (h->mode == RR_MODE_AUTO && rr_use_gemm_path(h, nq)) ? RR_GEMM_QCHUNK : RR_QCHUNK;
 }
@@ -1972,6 +1996,30 @@ extern "C" int rr_federation_search(rr_index_t* const* idx, int n_sources, const
     // sources that chunk the batch alike share their launches, RR_FED_MAX at a time
     bool done[256] = {};
     RR_REQUIRE(n_sources <= 256, "rr_federation_search: more than 256 sources");
+    {
+        rr_pad_args pa = {};
+        int n_empty = 0;
+        for (int s = 0; s < n_sources; ++s)
+            if (idx[s]->n == 0) {
+                done[s] = true;
+                pa.empty[s >> 6] |= 1ull << (s & 63);
+                ++n_empty;
+            }
+        if (n_empty > 0 && n_sources > 1) {
+            pa.D = D_dev;
+            pa.I = I_dev;
+            pa.nq = nq;
+            pa.out_stride = out_stride;
+            pa.k = k;
+            pa.n_sources = n_sources;
+            const int64_t total = nq * (int64_t)n_sources * k;
+            const unsigned blocks = (unsigned)std::min<int64_t>((total + 255) / 256, (int64_t)idx[0]->sm_count * 8);
+            RR_CUDA_CHECK(rr_launch_pdl(rr_fill_padding_kernel, dim3(blocks), dim3(256), 0, stream, pa));
+            rr_count_launch(1);
+        } else if (n_empty > 0) {
+            done[0] = false;  // a lone empty index keeps the plain path (index.search on an empty IndexFlatIP)
+        }
+    }
     for (int s0 = 0; s0 < n_sources; ++s0) {
         if (done[s0]) continue;
         const int64_t chunk = rr_chunk_size(idx[s0], nq);
