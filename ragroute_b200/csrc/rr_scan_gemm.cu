@@ -719,7 +719,10 @@ int rr_gemm_scan_list_depth(const rr_index* h, int nq) {
     // slices: with t query tiles the slices (and lists per query) shrink t-fold and 8-entry lists no longer hold
     // the k' = 128 candidates the finalize wants.  "gemm_depth" (testing knob) forces 8 or 32.
     if (h->gemm_depth == 8 || h->gemm_depth == 32) return h->gemm_depth;
-    const bool small_shard = h->n <= (int64_t)h->sm_count * 16384 && h->n >= 64 * (int64_t)kNT;
+    // (at least ~4 corpus tiles per list: with fewer rows per list than that a list's 8th-best is too close to the
+    // corpus-wide k-th best and certificates start to fail -- seen at 8 GPUs on 15 k-row shards -- while the
+    // cold-start cost that short lists avoid is small there anyway)
+    const bool small_shard = h->n <= (int64_t)h->sm_count * 16384 && h->n >= (int64_t)h->sm_count * 4 * kNT;
     return (small_shard && nq <= 2 * kQTile) ? 8 : kDepth;
 }
 
