@@ -91,7 +91,9 @@ int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
  * passes of <= 64 queries, 2 = queries-in-TMEM scan with one CTA per 128-query tile,
  * 3 = the same on CTA pairs), "gemm_tmem_all" (testing: 0 = keep the two-accumulator layout of the
  * queries-in-TMEM scan even for <= 128 queries), "gemm_depth" (testing: entries per candidate list of the
- * queries-in-TMEM scan, 8 or 32; 0 = automatic: 8 for shards of <= 16 k rows per list) */
+ * queries-in-TMEM scan, 8 or 32; 0 = automatic: 8 for shards of <= 16 k rows per list), "lockstep"
+ * (default 4: the work units of a queries-in-TMEM scan that stream the same corpus slice for different
+ * query tiles stay within that many tiles of each other, so every tile comes from HBM once; 0 = free running) */
 int rr_index_set_param(rr_index_t* h, const char* name, double value);
 
 /* index.search(x, k) (data_source.py:158,186,203) on device buffers:

@@ -1257,6 +1257,8 @@ extern "C" int rr_index_create(int d, int64_t capacity_rows, int device, rr_inde
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->add_event, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaMalloc(&h->d_nfail_total, 32);
     if (e == cudaSuccess) e = cudaMemset(h->d_nfail_total, 0, 32);
+    if (e == cudaSuccess) e = cudaMalloc(&h->scan_progress, RR_MAX_SCAN_UNITS * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(h->scan_progress, 0, RR_MAX_SCAN_UNITS * sizeof(unsigned long long));
     if (e != cudaSuccess) {
         rr_set_error("rr_index_create: %s", cudaGetErrorString(e));
         rr_index_destroy(h);
@@ -1285,6 +1287,7 @@ extern "C" int rr_index_destroy(rr_index_t* h) {
     cudaFree(h->lo);
     cudaFree(h->max_norm_bits);
     cudaFree(h->d_nfail_total);
+    cudaFree(h->scan_progress);
     cudaFree(h->scratch);
     cudaFree(h->stage);
     if (h->pin) cudaFreeHost(h->pin);
@@ -1448,6 +1451,9 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
         h->gemm_depth = (int)value;
     } else if (!strcmp(name, "gemm_tmem_all")) {
         h->gemm_tmem_all = value != 0;
+    } else if (!strcmp(name, "lockstep")) {
+        RR_REQUIRE(value >= 0 && value <= 4096, "lockstep must be 0 (off) or a window of 1 ... 4096 corpus tiles");
+        h->lockstep = (int)value;
     } else {
         rr_set_error("rr_index_set_param: unknown parameter '%s'", name);
         return RR_ERR_INVALID;

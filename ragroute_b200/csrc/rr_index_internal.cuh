@@ -22,6 +22,7 @@ constexpr int RR_GEMM_LIST_DEPTH = 32; // entries per (CTA, query) list of the l
 constexpr int RR_GEMM_QCHUNK = 2048;   // queries per chunk on the large-batch path
 constexpr int RR_PATH_AUTO = 0, RR_PATH_SMALL = 1, RR_PATH_GEMM = 2, RR_PATH_GEMM_PAIR = 3;  // set_param "scan_path"
 constexpr int RR_EXACT_MAX_QSUB = 16;  // queries per exact-scan launch
+constexpr int RR_MAX_SCAN_UNITS = 256; // work units (CTAs or CTA pairs) of a queries-in-TMEM scan launch
 
 struct rr_index {
     int d = 0;
@@ -47,6 +48,9 @@ struct rr_index {
     int scan_path = RR_PATH_AUTO;
     int gemm_depth = 0;     // 0 = automatic list depth of the queries-in-TMEM scan (8 for small shards, else 32)
     int gemm_tmem_all = 1;  // <= 128 queries: whole query tile in TMEM, one accumulator stage (testing knob)
+    int lockstep = 4;       // queries-in-TMEM scan: units sharing a corpus slice stay within this many tiles of each other (0 = off)
+    unsigned long long* scan_progress = nullptr;  // device, [RR_MAX_SCAN_UNITS]: (launch number << 32) | tiles issued
+    uint32_t scan_seq = 0;                        // launch number of the last queries-in-TMEM scan
 
     // per-search scratch (grow-only)
     void* scratch = nullptr;

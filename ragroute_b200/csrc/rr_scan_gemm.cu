@@ -82,6 +82,11 @@ struct GemmParams {
     int min_active, max_active;  // run only if min_active <= routed queries <= max_active (see rr_gemm_scan_launch)
     int chained;                 // 1: directly follows another scan of the same step (PDL, see rr_scan_tc.cu)
     int trace;                   // RR_TRACE: block 0 records a timeline (debugging aid)
+    // lockstep of the units that share a corpus slice (see the producer): progress[unit] = progress_base + tiles
+    // issued, progress_base = launch number << 32 (entries of earlier launches read as "not started"); NULL = off
+    unsigned long long* progress;
+    unsigned long long progress_base;
+    int lock_window;  // tiles a unit's producer may run ahead of the slowest unit of its slice
     float* cand_s;  // [compact query][slice][kDepth]
     uint32_t* cand_r;
     int64_t cand_stride;
@@ -116,6 +121,20 @@ __device__ __forceinline__ void trace_ev(int on, int tag, int tile) {
 // Drain the pending queues of a warp: round i inserts the i-th pending survivor of every thread
 // that has one.  Out of line: it runs for a fraction of the tiles.
 constexpr int kPend = 16;  // pending slots per thread
+// Lockstep: a unit's producer does not run more than lock_window corpus tiles ahead of the slowest unit sharing its
+// slice, polling at most kLockPolls times per tile (bounded: a sibling whose CTA has not started yet -- the
+// previous scan of the chain still holds its SM -- delays a tile by ~50 us at most, it never blocks it).
+constexpr int kLockPolls = 48;
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// (a max, not a store: when two chunks of one batch are scanned back to back, the second launch's units start
+// while the first's are still running and publish to the same entries; an entry never goes back to the older launch)
+__device__ __forceinline__ void red_max_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 // COLLECT mode: the pending survivors go to the query's global row list (thresholds are fixed).
 __device__ __noinline__ void epi_collect(int cnt, int qg, const GemmParams& p, const uint32_t* pr, int t) {
@@ -307,7 +326,23 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 else mbar_arrive(smem_u32(bar_a));
             }
         }
+        // Lockstep (nqt > 1): the nqt units of a slice stream the same tiles and only the first read of a tile
+        // should come from HBM.  Free running they drift apart -- a fraction of a percent in speed is tens of
+        // tiles over a 25 ms launch, more than L2 holds of the 18 x nqt streams -- and every unit ends up reading
+        // its own copy from HBM (ncu on the routed federation at batch 2048: 2.63x the algorithmic DRAM bytes).
+        // So each leader producer publishes how many tiles it has issued and waits (bounded) while the slowest
+        // unit of its slice is more than lock_window tiles behind.  The kernel ends with its slowest unit either
+        // way; the peer CTA of a pair follows its leader through the shared ring.
+        const bool lockstep = nqt > 1 && p.progress != nullptr && rank == 0;
+        const unsigned long long* prog_sib = p.progress + slice * nqt + min(lane, nqt - 1);
+        unsigned long long issued = p.progress_base;
+        const unsigned long long window = (unsigned long long)p.lock_window;
         for (int tile = slice; tile < p.n_tiles; tile += n_slices) {
+            unsigned long long sib = 0;
+            if (lockstep) {
+                if (elect_one_sync()) red_max_u64(p.progress + unit, issued);
+                sib = ld_relaxed_u64(prog_sib);  // in flight under this tile's TMA issue; looked at after it
+            }
             for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
                 const int nk = min(kStageKc, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
@@ -330,6 +365,15 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 if (++stage == p.stages) {
                     stage = 0;
                     phase ^= 1u;
+                }
+            }
+            ++issued;
+            if (lockstep) {
+#pragma unroll 1
+                for (int poll = 0; poll < kLockPolls; ++poll) {
+                    if (!__any_sync(RR_FULL, sib + window < issued)) break;
+                    __nanosleep(400);
+                    sib = ld_relaxed_u64(prog_sib);
                 }
             }
         }
@@ -801,6 +845,12 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     p.cand_stride = cand_stride;
     p.min_active = min_active;
     p.max_active = max_active;
+    static const char* lockstep_env = getenv("RR_LOCKSTEP");  // A/B switch for measurements: window in tiles, 0 = off
+    const int window = lockstep_env ? atoi(lockstep_env) : h->lockstep;
+    const bool lockstep = window > 0 && h->scan_progress != nullptr && h->sm_count <= RR_MAX_SCAN_UNITS;
+    p.progress = lockstep ? h->scan_progress : nullptr;
+    p.lock_window = window;
+    p.progress_base = (unsigned long long)(++h->scan_seq) << 32;
     static const int trace_on = getenv("RR_TRACE") != nullptr;
     p.trace = trace_on;
     p.theta = collect ? collect->theta : nullptr;

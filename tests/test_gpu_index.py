@@ -389,6 +389,27 @@ def test_gemm_path_medrag_shaped_no_rescans_and_equals_small_path(faiss):
         oracle.compare_topk(D[:40], I[:40], Dr, Ir, x=q[:40], xb=xb)
 
 
+@pytest.mark.parametrize("nq,path", [(600, 3), (2048, 3), (300, 2), (900, 0)])
+def test_gemm_path_lockstep_does_not_change_results(faiss, nq, path):
+    """The lockstep of the units sharing a corpus slice (several query tiles: 2 ... 8 siblings per slice) only paces
+    their TMA producers: results are bit-identical with it switched off, and no launch hangs or times out."""
+    d, k = 768, 32
+    xb = syn.corpus_rows(3, 90000, d)
+    q = syn.queries(nq, d, [3], seed=nq)
+    out = []
+    for lockstep in (4, 0, 1):                 # default window, free running, the tightest window
+        ix = _gemm_index(faiss, xb, path)
+        ix.set_param("lockstep", lockstep)
+        for _ in range(3):                     # repeated launches on one handle: the launch number keeps counting
+            D, I = ix.search(q, k)
+        assert ix.stats()["exact_rescans"] == 0
+        out.append((D, I))
+    for D, I in out[1:]:
+        assert np.array_equal(I, out[0][1]) and np.array_equal(D, out[0][0])
+    De, Ie = _index(faiss, xb, "exact").search(q[:64], k)
+    assert np.array_equal(out[0][1][:64], Ie) and np.array_equal(out[0][0][:64], De)
+
+
 def test_gemm_path_mask_chunks_and_default_dispatch(faiss):
     d, k = 768, 10
     xb = syn.corpus_rows(1, 30000, d)
