@@ -218,12 +218,12 @@ class CpuReference:
     ROW SAMPLE (proportional, >= 1 M rows in total by default: far beyond the caches); the reported
     queries/s is the measured rate scaled by sample_rows / total_rows (a flat scan is linear in N)."""
 
-    def __init__(self, spec: Spec, sample_rows_total: int):
+    def __init__(self, spec: Spec, sample_rows_total: int, routing: str = "ragroute"):
         from oracle import flat_ip, rerank_ref, router_ref
         from ragroute_b200 import synthetic as syn
         flat_ip.build()
         self.flat_ip, self.rerank_ref, self.router_ref = flat_ip, rerank_ref, router_ref
-        self.spec = spec
+        self.spec, self.routing = spec, routing
         self.cores = os.cpu_count() or 1
         self.plan = cpu_sample_plan(spec.rows, sample_rows_total)
         t0 = time.time()
@@ -252,8 +252,8 @@ class CpuReference:
         runs, one query at a time on one thread (data_source.py:114,186)."""
         s = self.spec
         B = next(iter(q.values())).shape[0]
-        mask = np.zeros((B, len(s.names)), dtype=bool)
-        for b in range(B):  # the reference routes one query at a time (router.py:212-214)
+        mask = np.ones((B, len(s.names)), dtype=bool)  # routing "all": every source, no router (router.py:226-227)
+        for b in range(B if self.routing == "ragroute" else 0):  # the reference routes one query at a time (router.py:212-214)
             mask[b] = self._route_one({m: q[m][b] for m in q})[0]
         per_src = {}
         for si, n in enumerate(s.names):
@@ -300,14 +300,15 @@ class CpuReference:
                 f"source); queries/s scaled linearly in rows to the full workload")
 
 
-def cpu_baseline_legs(spec: Spec, batch: int, sample_rows: int, steps: int, warmup: int, deployed_queries: int = 16):
+def cpu_baseline_legs(spec: Spec, batch: int, sample_rows: int, steps: int, warmup: int, deployed_queries: int = 16,
+                      routing: str = "ragroute"):
     """Both CPU figures: FAISS given the same batch (all cores) and the reference as
     deployed (nq = 1, one thread)."""
     t0 = time.time()
-    ref = CpuReference(spec, sample_rows)
+    ref = CpuReference(spec, sample_rows, routing)
     qps_b, ms_b, dens_b = ref.run(batch, steps, warmup, "batch")
     qps_d, ms_d, dens_d = ref.run(min(batch, deployed_queries), 1, 0, "deployed", n_threads=1)
-    nq_note = ("blocked sgemm (OpenBLAS) + heap pass, FAISS' nq >= 20 branch" if batch * 0.4 >= 20
+    nq_note = ("blocked sgemm (OpenBLAS) + heap pass, FAISS' nq >= 20 branch" if batch * dens_b >= 20
                else "sequential scan, OpenMP over queries, FAISS' nq < 20 branch")
     same = {"value": qps_b, "unit": UNIT, "cores": ref.cores, "kind": "port",
             "sample": f"{ref.sample_text()}; batch {batch}, {steps} timed steps, routed pairs only (mask density "
@@ -323,7 +324,7 @@ def reference_main(args, spec: Spec):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    ref = CpuReference(spec, args.cpu_sample_rows)
+    ref = CpuReference(spec, args.cpu_sample_rows, args.routing)
     qps, ms_sample, dens = ref.run(args.batch, args.steps, args.warmup, "batch")
     sample = (f"{ref.sample_text()}; batch {args.batch}, FAISS-restated search of routed pairs only (mask density "
               f"{dens:.2f}) with FAISS' own dispatch (nq >= 20: blocked sgemm + heap pass; below: sequential scan), "
@@ -781,7 +782,7 @@ def gpu_main(args, spec: Spec):
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_baseline = cpu_baseline_legs(spec, B, args.cpu_sample_rows, steps=3, warmup=1)
+        cpu_baseline = cpu_baseline_legs(spec, B, args.cpu_sample_rows, steps=3, warmup=1, routing=args.routing)
 
     if rank == 0:
         ms_step = dev_run["ms_total"] / args.steps
@@ -842,7 +843,9 @@ def main():
     ap.add_argument("--batch", type=int, default=0,
                     help="queries per step (default 2048; feb4rag16: 64 in flight); <= 64 is the HBM-bound regime, "
                          ">= 1024 the tensor-bound one")
-    ap.add_argument("--routing", default="ragroute", choices=["ragroute", "all"])
+    ap.add_argument("--routing", default=None, choices=["ragroute", "all"],
+                    help="default: ragroute; 'all' (no router in the step, every query searches every source) for the "
+                         "textbooks workload = BASELINE configs[0], one source alone")
     ap.add_argument("--rows-scale", type=float, default=1.0, help="scale every source's row count (debug)")
     ap.add_argument("--sweep", default=None, help="comma separated extra batch sizes ('' = none; default per workload)")
     ap.add_argument("--sweep-ms-budget", type=float, default=3000.0)
@@ -863,6 +866,8 @@ def main():
         args.batch = 64 if workload == "feb4rag16" else 2048
     if args.sweep is None:
         args.sweep = DEFAULT_SWEEP[workload]
+    if args.routing is None:
+        args.routing = "all" if workload == "textbooks" else "ragroute"
     if workload == "feb4rag16" and args.rows_scale != 1.0:
         raise SystemExit("bench.py: feb4rag16 has a fixed layout (--rows-scale is for the MedRAG workloads)")
     spec = make_spec(workload, args.rows_scale)

@@ -1451,6 +1451,9 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
         h->gemm_depth = (int)value;
     } else if (!strcmp(name, "gemm_tmem_all")) {
         h->gemm_tmem_all = value != 0;
+    } else if (!strcmp(name, "gemm_stage_kc")) {
+        RR_REQUIRE(value == 2 || value == 4, "gemm_stage_kc must be 2 or 4");
+        h->gemm_stage_kc = (int)value;
     } else if (!strcmp(name, "lockstep")) {
         RR_REQUIRE(value >= 0 && value <= 4096, "lockstep must be 0 (off) or a window of 1 ... 4096 corpus tiles");
         h->lockstep = (int)value;

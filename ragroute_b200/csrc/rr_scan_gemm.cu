@@ -47,8 +47,10 @@ using namespace rr_ptx;
 
 constexpr int kNT = RR_GEMM_TILE_ROWS;               // corpus rows per MMA (UMMA N)
 constexpr int kChunkBytes = kNT * RR_TC_KCHUNK * 2;  // one TMA box: 128 rows x 64 k = 16 KB
-constexpr int kStageKc = 2;                          // K-chunks per pipeline stage: one barrier wait per 8 MMAs
-constexpr int kStageBytes = kStageKc * kChunkBytes;  // 32 KB
+// K-chunks per pipeline stage (template parameter SKC): 2 = one barrier wait + one commit per 8 MMAs (32 KB stages
+// per query-tile unit); 4 = per 16 MMAs (64 KB stages, CTA pairs in the tensor-bound regime: every stage boundary
+// costs the tensor pipe ~120-150 idle cycles, profiles/microbench/r01_umma_pipe.txt)
+constexpr int kStageKc = 2;
 constexpr int kDepth = RR_GEMM_LIST_DEPTH;
 constexpr int kQTile = RR_GEMM_QTILE;  // 128 queries = TMEM lanes
 constexpr int kThreads = 192;
@@ -208,7 +210,7 @@ static_assert(kNT == RR_TC_TILE_ROWS, "both scan kernels share the 128-row TMA b
 // list), where a cold list of 32 lets ~32 (1 + ln(rows / 32)) rows through the insert path -- ~170 SIMT rounds
 // per warp on a 125 k-row corpus, 80 us of a launch whose HBM time is 29 us (RR_TRACE timeline) -- while
 // 148 lists x 8 still hold far more than the k' = 128 candidates the finalize wants.
-template <int CG, bool COLLECT, int DEPTH>
+template <int CG, bool COLLECT, int DEPTH, int SKC>
 __global__ void __launch_bounds__(kThreads, 1)
 rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_q,
                     const GemmParams p) {
@@ -246,7 +248,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
     // corpus rows / bytes of THIS CTA per tile chunk: all 128 rows (16 KB) or, in a pair, its 64 (8 KB)
     constexpr int kRowsCta = kNT / CG;
     constexpr int kChunkB = kChunkBytes / CG;
-    constexpr int kStageB = kStageKc * kChunkB;
+    constexpr int kStageB = SKC * kChunkB;
 
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) &
@@ -343,8 +345,8 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                 if (elect_one_sync()) red_max_u64(p.progress + unit, issued);
                 sib = ld_relaxed_u64(prog_sib);  // in flight under this tile's TMA issue; looked at after it
             }
-            for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
-                const int nk = min(kStageKc, p.num_kc - kc);
+            for (int kc = 0; kc < p.num_kc; kc += SKC) {
+                const int nk = min(SKC, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_empty + stage), phase ^ 1u);
                 trace_ev(tr && kc == 0, 1, tile);  // producer: first stage of the tile is free
                 if (elect_one_sync()) {
@@ -393,11 +395,11 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
             tc_fence_after();
             trace_ev(tr, 3, tile);  // MMA warp: accumulator free
             const uint32_t d_tmem = acc_base + (uint32_t)(acc * kNT);
-            for (int kc = 0; kc < p.num_kc; kc += kStageKc) {
-                const int nk = min(kStageKc, p.num_kc - kc);
+            for (int kc = 0; kc < p.num_kc; kc += SKC) {
+                const int nk = min(SKC, p.num_kc - kc);
                 mbar_wait(smem_u32(bar_full + stage), phase);
                 tc_fence_after();
-                trace_ev(tr && (kc == 0 || kc + kStageKc >= p.num_kc), 4, tile);  // MMA warp: first / last stage of the tile landed
+                trace_ev(tr && (kc == 0 || kc + SKC >= p.num_kc), 4, tile);  // MMA warp: first / last stage of the tile landed
                 const uint64_t b_desc = kUmmaDescSw128Hi | (uint64_t)(((x_base + stage * kStageB) >> 4) & 0x3FFFu);
                 const uint32_t a_tmem = tmem_base + (uint32_t)(kc * 32);
                 const uint64_t a_desc =
@@ -407,7 +409,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     // all-TMEM or all-smem
                     if (kc < p.a_tmem_kc) {  // A from tensor memory
 #pragma unroll
-                        for (int c = 0; c < kStageKc; ++c) {
+                        for (int c = 0; c < SKC; ++c) {
                             if (c < nk) {
                                 const uint32_t at = a_tmem + c * 32;
                                 const uint64_t bd = b_desc + (uint64_t)(c * (kChunkB >> 4));
@@ -426,7 +428,7 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                         }
                     } else {  // A from shared memory
 #pragma unroll
-                        for (int c = 0; c < kStageKc; ++c) {
+                        for (int c = 0; c < SKC; ++c) {
                             if (c < nk) {
                                 const uint64_t ad = a_desc + (uint64_t)(c * (kChunkBytes >> 4));
                                 const uint64_t bd = b_desc + (uint64_t)(c * (kChunkB >> 4));
@@ -446,10 +448,10 @@ rr_gemm_scan_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_con
                     }
                     if (CG == 2) {  // both CTAs' stage / accumulator barriers at once
                         umma_commit_2cta(smem_u32(bar_empty + stage));
-                        if (kc + kStageKc >= p.num_kc) umma_commit_2cta(smem_u32(bar_acc_full + acc));
+                        if (kc + SKC >= p.num_kc) umma_commit_2cta(smem_u32(bar_acc_full + acc));
                     } else {
                         umma_commit(smem_u32(bar_empty + stage));  // frees the smem stage when the MMAs retire
-                        if (kc + kStageKc >= p.num_kc) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
+                        if (kc + SKC >= p.num_kc) umma_commit(smem_u32(bar_acc_full + acc));  // accumulator complete
                     }
                 }
                 __syncwarp();
@@ -721,10 +723,10 @@ bool rr_gemm_scan_supported(const rr_index* h) {
 
 int rr_gemm_scan_max_lists(const rr_index* h) { return h->sm_count; }
 
-template <int CG, bool COLLECT, int DEPTH>
+template <int CG, bool COLLECT, int DEPTH, int SKC = kStageKc>
 static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, GemmParams p, bool chain,
                      cudaStream_t stream) {
-    const size_t stage_b = (size_t)kStageBytes / CG;
+    const size_t stage_b = (size_t)SKC * kChunkBytes / CG;
     const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
                          (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
     p.stages = (int)std::min<size_t>(kMaxStages, ((size_t)kSmemLimit - fixed) / stage_b);
@@ -733,7 +735,7 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     const size_t smem = fixed + (size_t)p.stages * stage_b;
     static std::atomic<bool> attr_done[RR_MAX_DEVICES];  // per (instantiation, device); a double set is harmless
     if (!attr_done[h->device].load(std::memory_order_acquire)) {
-        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RR_CUDA_CHECK(cudaFuncSetAttribute(rr_gemm_scan_kernel<CG, COLLECT, DEPTH, SKC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            kSmemLimit));
         attr_done[h->device].store(true, std::memory_order_release);
     }
@@ -753,7 +755,7 @@ static int launch_cg(rr_index* h, const CUtensorMap& tx, const CUtensorMap& tq, 
     cfg.attrs = attr;
     cfg.numAttrs = rr_pdl_enabled() ? 2 : 1;
     p.chained = (chain && rr_pdl_enabled()) ? 1 : 0;
-    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT, DEPTH>, tx, tq, p));
+    RR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, rr_gemm_scan_kernel<CG, COLLECT, DEPTH, SKC>, tx, tq, p));
     return RR_OK;
 }
 
@@ -871,6 +873,17 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     if (rr_gemm_scan_list_depth(h, nq) == 8)
         return cta_group == 2 ? launch_cg<2, false, 8>(h, h->tmap_hi64, tq, p, chain, stream)
                               : launch_cg<1, false, 8>(h, h->tmap_hi, tq, p, chain, stream);
+    // 64 KB stages (one barrier round trip and one commit per 16 MMAs instead of 8) for CTA pairs on batches that
+    // can hold several query tiles -- the tensor-bound regime -- when at least three such stages fit beside the
+    // query tile's tail (d_pad <= 768) and the tile's TMEM / shared-memory split falls on a stage boundary
+    static const char* skc_env = getenv("RR_STAGE_KC");  // A/B switch for measurements
+    const int skc = skc_env ? atoi(skc_env) : h->gemm_stage_kc;
+    if (cta_group == 2 && skc == 4 && nq > 2 * kQTile && (p.a_smem_kc == 0 || p.a_tmem_kc % 4 == 0)) {
+        const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
+                             (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
+        if (fixed + 3 * (size_t)(4 * kChunkBytes / 2) <= (size_t)kSmemLimit)
+            return launch_cg<2, false, kDepth, 4>(h, h->tmap_hi64, tq, p, chain, stream);
+    }
     return cta_group == 2 ? launch_cg<2, false, kDepth>(h, h->tmap_hi64, tq, p, chain, stream)
                           : launch_cg<1, false, kDepth>(h, h->tmap_hi, tq, p, chain, stream);
 }

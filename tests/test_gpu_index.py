@@ -410,6 +410,27 @@ def test_gemm_path_lockstep_does_not_change_results(faiss, nq, path):
     assert np.array_equal(out[0][1][:64], Ie) and np.array_equal(out[0][0][:64], De)
 
 
+@pytest.mark.parametrize("n,d,nq,path", [(60000, 768, 700, 3), (60000, 768, 2048, 0), (40000, 384, 600, 3),
+                                         (30000, 640, 300, 3), (20000, 1024, 520, 3), (9000, 100, 257, 3)])
+def test_gemm_path_64k_stages_agree_with_exact(faiss, n, d, nq, path):
+    """CTA pairs with 64 KB TMA stages (16 MMAs per barrier round trip; batches > 256, d_pad <= 768 -- wider rows fall
+    back to 32 KB stages): bit-identical to the exact mode and to the 32 KB-stage launch, no certificate failure."""
+    k = 32 if d == 768 else 10
+    rng = np.random.default_rng(n + d + nq)
+    xb = syn.corpus_rows(1, n, d) if d == 768 else rng.standard_normal((n, d), dtype=np.float32) / np.float32(np.sqrt(d))
+    q = syn.queries(nq, d, [1], seed=nq) if d == 768 else rng.standard_normal((nq, d), dtype=np.float32)
+    res = {}
+    for skc in (4, 2):
+        ix = _gemm_index(faiss, xb, path)
+        ix.set_param("gemm_stage_kc", skc)
+        res[skc] = ix.search(q, k)
+        if d == 768:
+            assert ix.stats()["exact_rescans"] == 0, f"certificate failed on benign data (stage_kc {skc}): {ix.stats()}"
+    assert np.array_equal(res[4][1], res[2][1]) and np.array_equal(res[4][0], res[2][0])
+    De, Ie = _index(faiss, xb, "exact").search(q[:96], k)
+    assert np.array_equal(res[4][1][:96], Ie) and np.array_equal(res[4][0][:96], De)
+
+
 def test_gemm_path_mask_chunks_and_default_dispatch(faiss):
     d, k = 768, 10
     xb = syn.corpus_rows(1, 30000, d)
