@@ -878,7 +878,9 @@ static int rr_gemm_scan_launch_one(rr_index* h, const uint16_t* qbf16_dev, int n
     // query tile's tail (d_pad <= 768) and the tile's TMEM / shared-memory split falls on a stage boundary
     static const char* skc_env = getenv("RR_STAGE_KC");  // A/B switch for measurements
     const int skc = skc_env ? atoi(skc_env) : h->gemm_stage_kc;
-    if (cta_group == 2 && skc == 4 && nq > 2 * kQTile && (p.a_smem_kc == 0 || p.a_tmem_kc % 4 == 0)) {
+    static const char* skc_minq_env = getenv("RR_STAGE_KC_MINQ");  // (measurements: smallest batch that takes them)
+    const int skc_min_nq = skc_minq_env ? atoi(skc_minq_env) : 2 * kQTile + 1;
+    if (cta_group == 2 && skc == 4 && nq >= skc_min_nq && (p.a_smem_kc == 0 || p.a_tmem_kc % 4 == 0)) {
         const size_t fixed = 1024 + (size_t)p.a_smem_kc * kChunkBytes + (size_t)(kDepth + kPend) * kQTile * 8 +
                              (2 * kMaxStages + 2 * kMaxAcc + 2) * 8 + 16;
         if (fixed + 3 * (size_t)(4 * kChunkBytes / 2) <= (size_t)kSmemLimit)
