@@ -1454,6 +1454,9 @@ extern "C" int rr_index_set_param(rr_index_t* h, const char* name, double value)
     } else if (!strcmp(name, "gemm_stage_kc")) {
         RR_REQUIRE(value == 2 || value == 4, "gemm_stage_kc must be 2 or 4");
         h->gemm_stage_kc = (int)value;
+    } else if (!strcmp(name, "gemm_pair_min")) {
+        RR_REQUIRE(value >= 2 && value <= RR_GEMM_QTILE + 1, "gemm_pair_min must be in [2, %d]", RR_GEMM_QTILE + 1);
+        h->gemm_pair_min = (int)value;
     } else if (!strcmp(name, "lockstep")) {
         RR_REQUIRE(value >= 0 && value <= 4096, "lockstep must be 0 (off) or a window of 1 ... 4096 corpus tiles");
         h->lockstep = (int)value;

@@ -49,6 +49,7 @@ struct rr_index {
     int gemm_depth = 0;     // 0 = automatic list depth of the queries-in-TMEM scan (8 for small shards, else 32)
     int gemm_tmem_all = 1;  // <= 128 queries: whole query tile in TMEM, one accumulator stage (testing knob)
     int gemm_stage_kc = 4;  // queries-in-TMEM scan on CTA pairs, batches > 256: K-chunks per TMA stage (4 = 64 KB stages; 2)
+    int gemm_pair_min = RR_GEMM_QTILE + 1;  // batches > 128: routed queries from which the device picks CTA pairs
     int lockstep = 4;       // queries-in-TMEM scan: units sharing a corpus slice stay within this many tiles of each other (0 = off)
     unsigned long long* scan_progress = nullptr;  // device, [RR_MAX_SCAN_UNITS]: (launch number << 32) | tiles issued
     uint32_t scan_seq = 0;                        // launch number of the last queries-in-TMEM scan

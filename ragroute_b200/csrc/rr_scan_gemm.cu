@@ -787,11 +787,14 @@ int rr_gemm_scan_launch(rr_index* h, const uint16_t* qbf16_dev, int nq, int cta_
         // Two launches, of which the device runs one: up to 128 ROUTED queries one CTA per corpus slice
         // (a single query tile: HBM-bound, 148 slices), more than that CTA pairs.  The host only knows the
         // batch size, not how many of its queries the router sent to this source.
+        // (the pair variant may take over below a full single tile: "gemm_pair_min" routed queries, <= 129)
+        static const char* pair_min_env = getenv("RR_PAIR_MIN");  // A/B switch for measurements
+        const int pair_min = std::min(kQTile + 1, std::max(2, pair_min_env ? atoi(pair_min_env) : h->gemm_pair_min));
         int rc = rr_gemm_scan_launch_one(h, qbf16_dev, nq, 1, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
-                                         1, kQTile, chain, stream);
+                                         1, pair_min - 1, chain, stream);
         if (rc != RR_OK) return rc;
         return rr_gemm_scan_launch_one(h, qbf16_dev, nq, 2, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
-                                       kQTile + 1, 0x7FFFFFFF, true, stream);
+                                       pair_min, 0x7FFFFFFF, true, stream);
     }
     return rr_gemm_scan_launch_one(h, qbf16_dev, nq, cta_group, ctl_dev, cand_s, cand_r, cand_stride, counters_dev, collect,
                                    1, 0x7FFFFFFF, chain, stream);
