@@ -27,12 +27,11 @@ except Exception as e: print(e)
 PY
 timeout 300 python scripts/gpu_dropin_latency.py > gpurun_out/r02k_dropin_latency.jsonl 2> gpurun_out/r02k_dropin.err; echo "dropin exit=$?"; cut -c1-230 gpurun_out/r02k_dropin_latency.jsonl
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-clustered-leg --verify-queries 0 --sweep=8,64"
+timeout 200 $CMD > gpurun_out/r02k_plain.json 2> gpurun_out/r02k_plain.err &&
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:rr_[^s]' -c 400 --csv --log-file gpurun_out/r02k_launches.csv $CMD > gpurun_out/r02k_ncu_l.out 2>&1
 echo "launch list exit=$?"
-CMD5="python bench.py --workload textbooks --batch 1 --steps 3 --warmup 3 --no-cpu-baseline --no-clustered-leg --verify-queries 0 --sweep=64"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k 'regex:rr_[^s]' -c 300 --csv --log-file gpurun_out/r02k_launches_small.csv $CMD5 > gpurun_out/r02k_ncu_l5.out 2>&1; echo "small launch list exit=$?"
-timeout 600 python bench.py --workload feb4rag16 --no-cpu-baseline > gpurun_out/r02k_bench_feb4rag16_1gpu.json 2> gpurun_out/r02k_bench_feb4rag16_1gpu.err; echo "feb4rag16 exit=$?"
 CMD2="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-clustered-leg --verify-queries 0 --sweep="
+timeout 200 $CMD2 > gpurun_out/r02k_plain2.json 2> gpurun_out/r02k_plain2.err &&
 timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:rr_gemm_scan_kernel<\(int\)2, \(bool\)0' -s 7 -c 1 -f -o gpurun_out/r02k_gemm_routed $CMD2 > gpurun_out/r02k_ncu2.out 2>&1; echo "gemm routed capture exit=$?"
 ncu -i gpurun_out/r02k_gemm_routed.ncu-rep --page raw --csv > gpurun_out/r02k_gemm_routed_raw.csv 2>/dev/null
 python scripts/ncu_keys.py gpurun_out/r02k_gemm_routed.ncu-rep 2>/dev/null | grep -E "Kernel Name|dram__bytes|time_duration|tensor_cycles|hit_rate"
