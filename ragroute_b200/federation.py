@@ -160,6 +160,7 @@ class Federation:
         self.d_max = int(d_max)
         self._packed: Optional[PackedLists] = None
         self._host_out: Dict[int, torch.Tensor] = {}  # pinned result buffers of search_host, per batch size
+        self._all_mask: Dict[tuple, torch.Tensor] = {}  # routing "all": the all-ones mask per (batch size, device)
         self._rng = random.Random(seed)
         if router is not None and routing == "ragroute":
             assert list(router.data_sources) == self.names, "router and federation must list sources in the same order"
@@ -171,7 +172,13 @@ class Federation:
         if self.routing == "ragroute":
             return self.router.select(q_router, self.threshold)
         if self.routing == "all":
-            return torch.ones((B, S), dtype=torch.uint8, device=q_router.device)
+            # (kept per batch size: a constant -- callers treat the returned mask as read-only -- and no fill
+            # kernel in front of every step)
+            key = (B, q_router.device)
+            m = self._all_mask.get(key)
+            if m is None:
+                m = self._all_mask[key] = torch.ones((B, S), dtype=torch.uint8, device=q_router.device)
+            return m
         if self.routing == "none":
             return torch.zeros((B, S), dtype=torch.uint8, device=q_router.device)
         m = np.zeros((B, S), dtype=np.uint8)
