@@ -93,7 +93,10 @@ int rr_index_set_id_offset(rr_index_t* h, int64_t offset);
  * queries-in-TMEM scan even for <= 128 queries), "gemm_depth" (testing: entries per candidate list of the
  * queries-in-TMEM scan, 8 or 32; 0 = automatic: 8 for shards of <= 16 k rows per list), "lockstep"
  * (default 4: the work units of a queries-in-TMEM scan that stream the same corpus slice for different
- * query tiles stay within that many tiles of each other, so every tile comes from HBM once; 0 = free running) */
+ * query tiles stay within that many tiles of each other, so every tile comes from HBM once; 0 = free running),
+ * "gemm_stage_kc" (4, default: CTA pairs on batches above 256 queries stream 64 KB TMA stages = 16 MMAs per
+ * barrier round trip; 2 = 32 KB stages everywhere), "gemm_pair_min" (129, default: batches above 128 queries
+ * take CTA pairs from that many ROUTED queries on, single CTAs below; 2 ... 129) */
 int rr_index_set_param(rr_index_t* h, const char* name, double value);
 
 /* index.search(x, k) (data_source.py:158,186,203) on device buffers:

@@ -94,6 +94,19 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["gpu_launches"] == 0 and d["vs_baseline"] is None
 
 
+def test_bench_textbooks_workload_is_one_source_alone_without_the_router():
+    """BASELINE configs[0] (Textbooks source alone): both arms default to routing 'all' -- every query searches the
+    one source, no router MLP in the step (router.py:226-227) -- while the routed workloads keep 'ragroute'."""
+    env = dict(os.environ, OMP_NUM_THREADS="2")
+    p = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--batch", "24", "--cpu-sample-rows", "4000", "--workload", "textbooks"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=REPO)
+    assert p.returncode == 0, p.stderr[-2000:]
+    d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+    assert d["config"]["workload"] == "textbooks" and d["config"]["routing"] == "all"
+    assert "mask density 1.00" in d["cpu_baseline"]["sample"] and d["value"] > 0
+
+
 def test_bench_gpu_arm_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
